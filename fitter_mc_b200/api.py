@@ -1,0 +1,274 @@
+"""ctypes binding of libfmc_b200.so (include/fmc_b200.h) + the reference-facing host layer.
+
+Reference interface mirrored here (bootstrap.f90):
+  initialise_model      365-387   -> initialise_model(model)
+  model_y               390-396   -> model_y(model, params, x)
+  derived_properties    399-407   -> derived_properties(model, params)
+  fit_data              215-226   -> fit_data(...)           (un-resampled fit, lines 288-291)
+  monte_carlo_fit_data  253-362   -> monte_carlo_fit_data(...)  (lines 288-341; printing is the driver's job)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+DEFAULT_SEED = 31415  # utils.f90:7
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_longlong)
+
+
+class FmcError(RuntimeError):
+    def __init__(self, code, where):
+        L = lib()
+        msg = L.fmc_strerror(code).decode()
+        detail = L.fmc_last_cuda_error().decode()
+        super().__init__("%s: %s (%d)%s" % (where, msg, code, (" -- " + detail) if detail else ""))
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, "libfmc_b200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError("libfmc_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C fitter_mc_b200 -j5`); fitter_mc_b200 has no CPU fallback")
+    L = C.CDLL(path)
+    L.fmc_strerror.restype = C.c_char_p
+    L.fmc_strerror.argtypes = [C.c_int]
+    L.fmc_last_cuda_error.restype = C.c_char_p
+    L.fmc_version.restype = C.c_char_p
+    L.fmc_model_count.restype = C.c_int
+    L.fmc_initialise_model.argtypes = [C.c_int, _ip, _ip, _dp, C.c_void_p, C.c_void_p, C.c_char_p]
+    L.fmc_model_y.restype = C.c_double
+    L.fmc_model_y.argtypes = [C.c_int, _dp, C.c_double]
+    L.fmc_derived_properties.argtypes = [C.c_int, _dp, _dp]
+    L.fmc_bootstrap_run.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, C.c_ulonglong,
+                                    C.c_longlong, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _lp, _lp]
+    L.fmc_fit_once.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _ip]
+    L.fmc_generate_offsets.argtypes = [C.c_ulonglong, C.c_longlong, C.c_longlong, C.c_int, _dp]
+    L.fmc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.fmc_destroy.argtypes = [C.c_void_p]
+    L.fmc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.fmc_set_data.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]
+    L.fmc_set_accumulator_dev.argtypes = [C.c_void_p, C.c_void_p]
+    L.fmc_accumulator_len.argtypes = [C.c_void_p]
+    L.fmc_launch.argtypes = [C.c_void_p, _dp, C.c_longlong, C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_int]
+    L.fmc_finish.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _lp, _lp]
+    L.fmc_decode_accumulator.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _lp, _lp, _lp]
+    L.fmc_last_kernel_ms.restype = C.c_float
+    L.fmc_last_kernel_ms.argtypes = [C.c_void_p]
+    L.fmc_last_launch_geometry.argtypes = [C.c_void_p, _ip]
+    L.fmc_measure_dfma_peak.argtypes = [C.c_int, C.c_int, _dp, C.POINTER(C.c_float)]
+    L.fmc_finalise_moments.argtypes = [C.c_int, C.c_longlong, _dp, _dp, _dp, _dp]
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _check(rc, where):
+    if rc != 0:
+        raise FmcError(rc, where)
+
+
+def model_count():
+    return lib().fmc_model_count()
+
+
+def initialise_model(model=0):
+    """bootstrap.f90:365-387: nparam, nprop, names and the initial parameter values."""
+    nparam, nprop = C.c_int(), C.c_int()
+    init = np.zeros(16)
+    pn = C.create_string_buffer(16 * 3)
+    qn = C.create_string_buffer(16 * 3)
+    name = C.create_string_buffer(32)
+    _check(lib().fmc_initialise_model(model, C.byref(nparam), C.byref(nprop), _d(init), pn, qn, name),
+           "fmc_initialise_model")
+    p, q = nparam.value, nprop.value
+    return dict(name=name.value.decode(), nparam=p, nprop=q, params_init=init[:p].copy(),
+                param_name=[pn.raw[3 * i:3 * i + 2].decode() for i in range(p)],
+                prop_name=[qn.raw[3 * i:3 * i + 2].decode() for i in range(q)])
+
+
+def model_y(model, params, x):
+    """bootstrap.f90:390-396 (host image of the device callback)."""
+    params = _f64(params)
+    L = lib()
+    xs = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    return np.array([L.fmc_model_y(model, _d(params), float(v)) for v in xs])
+
+
+def derived_properties(model, params):
+    """bootstrap.f90:399-407."""
+    info = initialise_model(model)
+    params = _f64(params)
+    props = np.zeros(max(info["nprop"], 1))
+    _check(lib().fmc_derived_properties(model, _d(params), _d(props)), "fmc_derived_properties")
+    return props[:info["nprop"]]
+
+
+def finalise_moments(nresample, s, s2):
+    """bootstrap.f90:328-341."""
+    s, s2 = _f64(s), _f64(s2)
+    mean, err = np.empty(len(s)), np.empty(len(s))
+    lib().fmc_finalise_moments(len(s), int(nresample), _d(s), _d(s2), _d(mean), _d(err))
+    return mean, err
+
+
+def fit_data(x, y, err_y, params, model=0):
+    """offset_data(.FALSE.); fit_data(params) -- bootstrap.f90:288-291, on the GPU.
+    Returns (params, [rc of the two nl2sno calls])."""
+    x, y, err_y = map(_f64, (x, y, err_y))
+    params = _f64(params).copy()
+    rc2 = np.zeros(2, dtype=np.int32)
+    _check(lib().fmc_fit_once(model, len(x), _d(x), _d(y), _d(err_y), _d(params), rc2.ctypes.data_as(_ip)),
+           "fmc_fit_once")
+    return params, rc2
+
+
+def generate_offsets(seed, first_counter, nresample, ndata):
+    z = np.empty((nresample, ndata))
+    _check(lib().fmc_generate_offsets(seed, first_counter, nresample, ndata, _d(z)), "fmc_generate_offsets")
+    return z
+
+
+def decode_accumulator(model, params_start, acc):
+    info = initialise_model(model)
+    p, q = info["nparam"], info["nprop"]
+    params_start, acc = _f64(params_start), _f64(acc)
+    out = dict(sum_p=np.zeros(p), sum_p2=np.zeros(p), sum_prop=np.zeros(max(q, 1)), sum_prop2=np.zeros(max(q, 1)),
+               rc_count=np.zeros(16, dtype=np.int64), totals=np.zeros(4, dtype=np.int64))
+    nfit = C.c_longlong(0)
+    _check(lib().fmc_decode_accumulator(model, _d(params_start), _d(acc), _d(out["sum_p"]), _d(out["sum_p2"]),
+                                        _d(out["sum_prop"]), _d(out["sum_prop2"]), C.byref(nfit),
+                                        out["rc_count"].ctypes.data_as(_lp), out["totals"].ctypes.data_as(_lp)),
+           "fmc_decode_accumulator")
+    out["nfit"] = nfit.value
+    out["sum_prop"], out["sum_prop2"] = out["sum_prop"][:q], out["sum_prop2"][:q]
+    return out
+
+
+def monte_carlo_fit_data(x, y, err_y, model=0, nrand_points=100000, seed=DEFAULT_SEED, first_counter=0,
+                         ngpus=1, params_init=None, z_inject=None, per_resample=False, initial_fit=True):
+    """monte_carlo_fit_data, bootstrap.f90:253-362, without the printing: initial fit on the raw
+    data (288-295), the bootstrap loop (297-330, one C-ABI call), means and Bessel errors (328-341)."""
+    info = initialise_model(model)
+    p, q = info["nparam"], info["nprop"]
+    x, y, err_y = map(_f64, (x, y, err_y))
+    start = _f64(info["params_init"] if params_init is None else params_init).copy()
+    rc_init = None
+    if initial_fit:
+        start, rc_init = fit_data(x, y, err_y, start, model)
+    n = int(nrand_points)
+    zi = None
+    if z_inject is not None:
+        zi = _f64(z_inject)
+        assert zi.shape == (n, len(x))
+    s = [np.zeros(p), np.zeros(p), np.zeros(max(q, 1)), np.zeros(max(q, 1))]
+    pout = np.zeros((n, p)) if per_resample else None
+    qout = np.zeros((n, max(q, 1))) if per_resample else None
+    rcc = np.zeros(16, dtype=np.int64)
+    tot = np.zeros(4, dtype=np.int64)
+    _check(lib().fmc_bootstrap_run(model, len(x), _d(x), _d(y), _d(err_y), _d(start), n, seed, first_counter, ngpus,
+                                   _d(zi), _d(s[0]), _d(s[1]), _d(s[2]), _d(s[3]), _d(pout), _d(qout),
+                                   rcc.ctypes.data_as(_lp), tot.ctypes.data_as(_lp)), "fmc_bootstrap_run")
+    params_opt, err_params_opt = finalise_moments(n, s[0], s[1])
+    props_opt, err_props_opt = finalise_moments(n, s[2][:q], s[3][:q])
+    return dict(info=info, params_fit=start, props_fit=derived_properties(model, start), rc_init=rc_init,
+                params_opt=params_opt, err_params_opt=err_params_opt, props_opt=props_opt,
+                err_props_opt=err_props_opt, sum_p=s[0], sum_p2=s[1], sum_prop=s[2][:q], sum_prop2=s[3][:q],
+                params=pout, props=None if qout is None else qout[:, :q], rc_count=rcc, totals=tot,
+                nrand_points=n)
+
+
+def measure_dfma_peak(device=0, iters=20000):
+    """Measured FP64 FMA peak of the device in TFLOP/s (register-resident DFMA chains)."""
+    t = C.c_double(0.0)
+    ms = C.c_float(0.0)
+    _check(lib().fmc_measure_dfma_peak(device, iters, C.byref(t), C.byref(ms)), "fmc_measure_dfma_peak")
+    return t.value, ms.value
+
+
+class Context:
+    """One GPU: resident data, a stream, asynchronous launches (fmc_create ... fmc_finish)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().fmc_create(C.byref(self._h), device), "fmc_create")
+        self.model = None
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().fmc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().fmc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "fmc_set_stream")
+
+    def set_data(self, model, x, y, err_y):
+        x, y, err_y = map(_f64, (x, y, err_y))
+        _check(lib().fmc_set_data(self._h, model, len(x), _d(x), _d(y), _d(err_y)), "fmc_set_data")
+        self.model = model
+        self.info = initialise_model(model)
+        self.ndata = len(x)
+
+    def accumulator_len(self):
+        return lib().fmc_accumulator_len(self._h)
+
+    def set_accumulator_dev(self, ptr):
+        _check(lib().fmc_set_accumulator_dev(self._h, C.c_void_p(ptr)), "fmc_set_accumulator_dev")
+
+    def launch(self, params_start, nresample, seed=DEFAULT_SEED, first_counter=0, z_inject_dev=None, keep=False):
+        self._start = _f64(params_start).copy()
+        self._nres = int(nresample)
+        self._keep = keep
+        _check(lib().fmc_launch(self._h, _d(self._start), self._nres, seed, first_counter,
+                                C.c_void_p(z_inject_dev) if z_inject_dev else None, 1 if keep else 0), "fmc_launch")
+
+    def finish(self):
+        p, q, n = self.info["nparam"], self.info["nprop"], self._nres
+        s = [np.zeros(p), np.zeros(p), np.zeros(max(q, 1)), np.zeros(max(q, 1))]
+        pout = np.zeros((n, p)) if self._keep else None
+        qout = np.zeros((n, max(q, 1))) if self._keep else None
+        cout = np.zeros((n, 2, 5), dtype=np.int32) if self._keep else None
+        rcc = np.zeros(16, dtype=np.int64)
+        tot = np.zeros(4, dtype=np.int64)
+        _check(lib().fmc_finish(self._h, _d(s[0]), _d(s[1]), _d(s[2]), _d(s[3]), _d(pout), _d(qout),
+                                None if cout is None else cout.ctypes.data_as(_ip),
+                                rcc.ctypes.data_as(_lp), tot.ctypes.data_as(_lp)), "fmc_finish")
+        return dict(sum_p=s[0], sum_p2=s[1], sum_prop=s[2][:q], sum_prop2=s[3][:q], params=pout,
+                    props=None if qout is None else qout[:, :q], counters=cout, rc_count=rcc, totals=tot)
+
+    def kernel_ms(self):
+        return float(lib().fmc_last_kernel_ms(self._h))
+
+    def geometry(self):
+        g = np.zeros(4, dtype=np.int32)
+        lib().fmc_last_launch_geometry(self._h, g.ctypes.data_as(_ip))
+        return dict(blocks=int(g[0]), threads=int(g[1]), blocks_per_sm=int(g[2]), sms=int(g[3]))

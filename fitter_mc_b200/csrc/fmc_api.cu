@@ -1,0 +1,592 @@
+// C ABI of libfmc_b200.so (declared in include/fmc_b200.h).  Host-side plumbing only:
+// device buffers, stream, launch geometry, decoding of the accumulator block.  All the
+// arithmetic of the hot path is in bootstrap_kernel.cuh / nl2_solver.cuh / pass_eval.cuh.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fmc_b200.h"
+#include "model_registry.cuh"
+
+using namespace fmc;
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+
+#define FMC_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      g_last_cuda_error = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+      return FMC_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+const std::vector<ModelEntry>& models() {
+  static const std::vector<ModelEntry> m = {fmc_entry_model0(), fmc_entry_model1(), fmc_entry_model2(),
+                                            fmc_entry_model3()};
+  return m;
+}
+
+int device_count() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    return 0;
+  }
+  return n;
+}
+
+__global__ void generate_offsets_kernel(unsigned long long seed, long long first, long long nres, int n,
+                                        double* __restrict__ z) {
+  const int nblk = (n + 3) / 4;
+  const long long total = nres * (long long)nblk;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / nblk;
+    const int b = (int)(t - r * nblk);
+    float zz[4];
+    normals4(seed, (unsigned long long)(first + r), (uint32_t)b, zz);
+    for (int m = 0; m < 4 && 4 * b + m < n; ++m) z[r * n + 4 * b + m] = (double)zz[m];
+  }
+}
+
+// Register-resident DFMA chains: the measured FP64 roofline denominator (MEASURED_PEAKS.json
+// has no FP64 entry; SURVEY.md section 8d asks for this microbenchmark).
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0,
+         x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fma(x0, a, b);
+      x1 = fma(x1, a, b);
+      x2 = fma(x2, a, b);
+      x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b);
+      x5 = fma(x5, a, b);
+      x6 = fma(x6, a, b);
+      x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace
+
+struct fmc_context {
+  int device = 0;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int model = -1, n = 0, n_pad = 0;
+  RowData* rows_dev = nullptr;
+  int rows_cap = 0;
+  double* acc_own = nullptr;
+  double* acc = nullptr;
+  int acc_n = 0;
+  unsigned long long* next_id_dev = nullptr;
+  double* params_out_dev = nullptr;
+  double* props_out_dev = nullptr;
+  int* counters_dev = nullptr;
+  long long out_cap = 0;
+  long long inflight = -1;
+  bool keep = false;
+  double start[16] = {0};
+  int geom[4] = {0, 0, 0, 0};
+  std::vector<RowData> rows_host;
+};
+
+extern "C" {
+
+const char* fmc_version(void) { return "fmc_b200 0.1 (sm_100a)"; }
+
+const char* fmc_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+const char* fmc_strerror(int code) {
+  switch (code) {
+    case FMC_OK: return "success";
+    case FMC_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case FMC_ERR_CUDA: return "a CUDA call failed (see fmc_last_cuda_error)";
+    case FMC_ERR_BAD_MODEL: return "model id out of range";
+    case FMC_ERR_BAD_ARG: return "invalid argument";
+    case FMC_ERR_NO_DATA: return "fmc_set_data has not been called";
+    case FMC_ERR_STATE: return "no launch in flight";
+    case FMC_ERR_ALLOC: return "allocation failed";
+    default: return "unknown error code";
+  }
+}
+
+int fmc_model_count(void) { return (int)models().size(); }
+
+int fmc_initialise_model(int model, int* nparam, int* nprop, double* params_init, char (*param_name)[3],
+                         char (*prop_name)[3], char* model_name32) {
+  if (model < 0 || model >= fmc_model_count()) return FMC_ERR_BAD_MODEL;
+  const ModelEntry& m = models()[model];
+  if (nparam) *nparam = m.nparam;
+  if (nprop) *nprop = m.nprop;
+  for (int i = 0; i < m.nparam; ++i) {
+    if (params_init) params_init[i] = m.init[i];
+    if (param_name) {
+      std::snprintf(param_name[i], 3, "%-2.2s", m.pnames[i] ? m.pnames[i] : "");
+    }
+  }
+  for (int i = 0; i < m.nprop; ++i)
+    if (prop_name) std::snprintf(prop_name[i], 3, "%-2.2s", m.qnames[i] ? m.qnames[i] : "");
+  if (model_name32) std::snprintf(model_name32, 32, "%s", m.name);
+  return FMC_OK;
+}
+
+double fmc_model_y(int model, const double* params, double x) {
+  if (model < 0 || model >= fmc_model_count()) return 0.0;
+  return models()[model].model_y(params, x);
+}
+
+int fmc_derived_properties(int model, const double* params, double* props) {
+  if (model < 0 || model >= fmc_model_count()) return FMC_ERR_BAD_MODEL;
+  models()[model].props(params, props);
+  return FMC_OK;
+}
+
+void fmc_finalise_moments(int k, long long nresample, const double* sum, const double* sum2, double* mean,
+                          double* err) {
+  const double rtemp = 1.0 / (double)nresample;  // bootstrap.f90:328-330
+  for (int i = 0; i < k; ++i) {
+    const double m = sum[i] * rtemp, m2 = sum2[i] * rtemp;
+    mean[i] = m;
+    if (nresample > 1) {
+      const double bessel = (double)nresample / (double)(nresample - 1);  // bootstrap.f90:334-337
+      err[i] = std::sqrt(std::fmax((m2 - m * m) * bessel, 0.0));
+    } else {
+      err[i] = 0.0;
+    }
+  }
+}
+
+int fmc_create(fmc_context** out, int device) {
+  if (!out) return FMC_ERR_BAD_ARG;
+  *out = nullptr;
+  const int ndev = device_count();
+  if (ndev <= 0) return FMC_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return FMC_ERR_BAD_ARG;
+  FMC_CUDA(cudaSetDevice(device));
+  fmc_context* c = new (std::nothrow) fmc_context();
+  if (!c) return FMC_ERR_ALLOC;
+  c->device = device;
+  cudaDeviceProp prop;
+  FMC_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  FMC_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  FMC_CUDA(cudaEventCreate(&c->ev0));
+  FMC_CUDA(cudaEventCreate(&c->ev1));
+  FMC_CUDA(cudaMalloc(&c->next_id_dev, sizeof(unsigned long long)));
+  c->acc_n = acc_len(FMC_MAX_PARAM, FMC_MAX_PARAM);
+  FMC_CUDA(cudaMalloc(&c->acc_own, sizeof(double) * c->acc_n));
+  c->acc = c->acc_own;
+  *out = c;
+  return FMC_OK;
+}
+
+int fmc_destroy(fmc_context* c) {
+  if (!c) return FMC_OK;
+  cudaSetDevice(c->device);
+  if (c->inflight >= 0) cudaStreamSynchronize(c->stream);
+  cudaFree(c->rows_dev);
+  cudaFree(c->acc_own);
+  cudaFree(c->next_id_dev);
+  cudaFree(c->params_out_dev);
+  cudaFree(c->props_out_dev);
+  cudaFree(c->counters_dev);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return FMC_OK;
+}
+
+int fmc_set_stream(fmc_context* c, void* cuda_stream) {
+  if (!c) return FMC_ERR_BAD_ARG;
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return FMC_OK;
+}
+
+int fmc_set_data(fmc_context* c, int model, int ndata, const double* x, const double* y, const double* err_y) {
+  if (!c || !x || !y || !err_y) return FMC_ERR_BAD_ARG;
+  if (model < 0 || model >= fmc_model_count()) return FMC_ERR_BAD_MODEL;
+  const ModelEntry& m = models()[model];
+  if (ndata < m.nparam || ndata < 1) return FMC_ERR_BAD_ARG;
+  for (int i = 0; i < ndata; ++i)
+    if (!(err_y[i] > 0.0)) return FMC_ERR_BAD_ARG;  // bootstrap.f90:134-138
+  FMC_CUDA(cudaSetDevice(c->device));
+  const int n_pad = (ndata + 3) / 4 * 4;
+  c->rows_host.resize(n_pad);
+  for (int i = 0; i < n_pad; ++i) {
+    RowData r;
+    if (i < ndata) {
+      r.x = x[i];
+      r.y = y[i];
+      r.err = err_y[i];
+      r.rerr = 1.0 / err_y[i];  // bootstrap.f90:140
+    } else {  // padding rows contribute exactly zero to every sum
+      r.x = x[ndata - 1];
+      r.y = 0.0;
+      r.err = 0.0;
+      r.rerr = 0.0;
+    }
+    c->rows_host[i] = r;
+  }
+  if (n_pad > c->rows_cap) {
+    cudaFree(c->rows_dev);
+    c->rows_dev = nullptr;
+    FMC_CUDA(cudaMalloc(&c->rows_dev, sizeof(RowData) * n_pad));
+    c->rows_cap = n_pad;
+  }
+  FMC_CUDA(cudaMemcpyAsync(c->rows_dev, c->rows_host.data(), sizeof(RowData) * n_pad, cudaMemcpyHostToDevice,
+                           c->stream));
+  FMC_CUDA(cudaStreamSynchronize(c->stream));
+  c->model = model;
+  c->n = ndata;
+  c->n_pad = n_pad;
+  return FMC_OK;
+}
+
+int fmc_accumulator_len(const fmc_context* c) {
+  if (!c || c->model < 0) return acc_len(FMC_MAX_PARAM, FMC_MAX_PARAM);
+  const ModelEntry& m = models()[c->model];
+  return acc_len(m.nparam, m.nprop);
+}
+
+int fmc_set_accumulator_dev(fmc_context* c, double* acc_dev) {
+  if (!c) return FMC_ERR_BAD_ARG;
+  c->acc = acc_dev ? acc_dev : c->acc_own;
+  return FMC_OK;
+}
+
+int fmc_launch(fmc_context* c, const double* params_start, long long nresample, unsigned long long seed,
+               long long first_counter, const double* z_inject_dev, int keep_per_resample) {
+  if (!c || !params_start || nresample < 0) return FMC_ERR_BAD_ARG;
+  if (c->model < 0) return FMC_ERR_NO_DATA;
+  const ModelEntry& m = models()[c->model];
+  FMC_CUDA(cudaSetDevice(c->device));
+  if (c->inflight >= 0) FMC_CUDA(cudaStreamSynchronize(c->stream));
+  const int P = m.nparam, Q = m.nprop;
+  c->keep = keep_per_resample != 0;
+  if (c->keep && nresample > c->out_cap) {
+    cudaFree(c->params_out_dev);
+    cudaFree(c->props_out_dev);
+    cudaFree(c->counters_dev);
+    c->params_out_dev = c->props_out_dev = nullptr;
+    c->counters_dev = nullptr;
+    c->out_cap = 0;
+    FMC_CUDA(cudaMalloc(&c->params_out_dev, sizeof(double) * P * nresample));
+    FMC_CUDA(cudaMalloc(&c->props_out_dev, sizeof(double) * (Q > 0 ? Q : 1) * nresample));
+    FMC_CUDA(cudaMalloc(&c->counters_dev, sizeof(int) * 10 * nresample));
+    c->out_cap = nresample;
+  }
+  KernelArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.rows = c->rows_dev;
+  a.n = c->n;
+  a.n_pad = c->n_pad;
+  for (int i = 0; i < P; ++i) {
+    a.start[i] = params_start[i];
+    c->start[i] = params_start[i];
+  }
+  a.seed = seed;
+  a.first = first_counter;
+  a.nres = nresample;
+  a.z_inject = z_inject_dev;
+  a.params_out = c->keep ? c->params_out_dev : nullptr;
+  a.props_out = c->keep ? c->props_out_dev : nullptr;
+  a.counters_out = c->keep ? c->counters_dev : nullptr;
+  a.next_id = c->next_id_dev;
+  a.acc = c->acc;
+
+  // data in shared memory when it fits (227 KB opt-in on B200), else through L1/L2
+  size_t shmem = sizeof(RowData) * (size_t)c->n_pad;
+  bool smem = shmem + 1024 <= (size_t)c->max_smem_optin;
+  if (!smem) shmem = 0;
+  const bool inject = z_inject_dev != nullptr;
+  int bps = 0;
+  FMC_CUDA(m.occupancy(inject, smem, shmem, &bps));
+  if (bps < 1) {
+    g_last_cuda_error = "kernel does not fit on an SM";
+    return FMC_ERR_CUDA;
+  }
+  // persistent grid: every SM full, threads take resamples from a shared counter
+  long long grid = (long long)c->num_sms * bps;
+  const long long need = (nresample + FMC_THREADS - 1) / FMC_THREADS;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  c->geom[0] = (int)grid;
+  c->geom[1] = FMC_THREADS;
+  c->geom[2] = bps;
+  c->geom[3] = c->num_sms;
+
+  FMC_CUDA(cudaMemsetAsync(c->next_id_dev, 0, sizeof(unsigned long long), c->stream));
+  FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
+  FMC_CUDA(cudaEventRecord(c->ev0, c->stream));
+  if (nresample > 0) FMC_CUDA(m.launch(a, inject, smem, (int)grid, shmem, c->stream));
+  FMC_CUDA(cudaEventRecord(c->ev1, c->stream));
+  c->inflight = nresample;
+  return FMC_OK;
+}
+
+int fmc_decode_accumulator(int model, const double* params_start, const double* acc, double* sum_p,
+                           double* sum_p2, double* sum_prop, double* sum_prop2, long long* nfit,
+                           long long* rc_count, long long* totals) {
+  if (model < 0 || model >= fmc_model_count()) return FMC_ERR_BAD_MODEL;
+  if (!params_start || !acc) return FMC_ERR_BAD_ARG;
+  const ModelEntry& m = models()[model];
+  const int P = m.nparam, Q = m.nprop, NM = 2 * (P + Q);
+  const double N = acc[NM + ACC_NFIT];
+  double cq[FMC_MAX_PARAM];
+  m.props(params_start, cq);
+  // sums were accumulated as sum(v - c), sum((v - c)^2) with c = value at params_start
+  for (int i = 0; i < P; ++i) {
+    const double c0 = params_start[i], s1 = acc[i], s2 = acc[P + i];
+    if (sum_p) sum_p[i] = N * c0 + s1;
+    if (sum_p2) sum_p2[i] = s2 + 2.0 * c0 * s1 + N * c0 * c0;
+  }
+  for (int i = 0; i < Q; ++i) {
+    const double c0 = cq[i], s1 = acc[2 * P + i], s2 = acc[2 * P + Q + i];
+    if (sum_prop) sum_prop[i] = N * c0 + s1;
+    if (sum_prop2) sum_prop2[i] = s2 + 2.0 * c0 * s1 + N * c0 * c0;
+  }
+  if (nfit) *nfit = (long long)(N + 0.5);
+  if (rc_count)
+    for (int i = 0; i < 16; ++i) rc_count[i] = (long long)(acc[NM + ACC_RC + i] + 0.5);
+  if (totals) {
+    totals[0] = (long long)(acc[NM + ACC_NFCALL] + 0.5);
+    totals[1] = (long long)(acc[NM + ACC_NGCALL] + 0.5);
+    totals[2] = (long long)(acc[NM + ACC_NITER] + 0.5);
+    totals[3] = (long long)(acc[NM + ACC_NPASS] + 0.5);
+  }
+  return FMC_OK;
+}
+
+int fmc_finish(fmc_context* c, double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,
+               double* params_out, double* props_out, int* counters_out, long long* rc_count,
+               long long* totals) {
+  if (!c) return FMC_ERR_BAD_ARG;
+  if (c->inflight < 0) return FMC_ERR_STATE;
+  const ModelEntry& m = models()[c->model];
+  const int P = m.nparam, Q = m.nprop;
+  FMC_CUDA(cudaSetDevice(c->device));
+  std::vector<double> acc(acc_len(P, Q));
+  FMC_CUDA(cudaMemcpyAsync(acc.data(), c->acc, sizeof(double) * acc.size(), cudaMemcpyDeviceToHost, c->stream));
+  const long long nres = c->inflight;
+  if (c->keep && nres > 0) {
+    if (params_out)
+      FMC_CUDA(cudaMemcpyAsync(params_out, c->params_out_dev, sizeof(double) * P * nres, cudaMemcpyDeviceToHost,
+                               c->stream));
+    if (props_out && Q > 0)
+      FMC_CUDA(cudaMemcpyAsync(props_out, c->props_out_dev, sizeof(double) * Q * nres, cudaMemcpyDeviceToHost,
+                               c->stream));
+    if (counters_out)
+      FMC_CUDA(cudaMemcpyAsync(counters_out, c->counters_dev, sizeof(int) * 10 * nres, cudaMemcpyDeviceToHost,
+                               c->stream));
+  }
+  FMC_CUDA(cudaStreamSynchronize(c->stream));
+  c->inflight = -1;
+  long long nfit = 0;
+  int rc = fmc_decode_accumulator(c->model, c->start, acc.data(), sum_p, sum_p2, sum_prop, sum_prop2, &nfit,
+                                  rc_count, totals);
+  if (rc != FMC_OK) return rc;
+  if (nfit != nres) {
+    g_last_cuda_error = "kernel finished " + std::to_string(nfit) + " of " + std::to_string(nres) + " fits";
+    return FMC_ERR_CUDA;
+  }
+  return FMC_OK;
+}
+
+float fmc_last_kernel_ms(fmc_context* c) {
+  if (!c) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+int fmc_last_launch_geometry(const fmc_context* c, int* out4) {
+  if (!c || !out4) return FMC_ERR_BAD_ARG;
+  for (int i = 0; i < 4; ++i) out4[i] = c->geom[i];
+  return FMC_OK;
+}
+
+// ---------------------------------------------------------------------------- one-shot API
+namespace {
+std::mutex g_ctx_mutex;
+std::vector<fmc_context*> g_ctx;  // one cached context per device
+
+int cached_context(int device, fmc_context** out) {
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  if ((int)g_ctx.size() <= device) g_ctx.resize(device + 1, nullptr);
+  if (!g_ctx[device]) {
+    int rc = fmc_create(&g_ctx[device], device);
+    if (rc != FMC_OK) return rc;
+  }
+  *out = g_ctx[device];
+  return FMC_OK;
+}
+}  // namespace
+
+int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, const double* err_y,
+                      const double* params_start, long long nresample, unsigned long long seed,
+                      long long first_counter, int ngpus, const double* z_inject, double* sum_p,
+                      double* sum_p2, double* sum_prop, double* sum_prop2, double* params_out,
+                      double* props_out, long long* rc_count, long long* totals) {
+  if (model < 0 || model >= fmc_model_count()) return FMC_ERR_BAD_MODEL;
+  if (!x || !y || !err_y || !params_start || nresample < 0 || ngpus < 0) return FMC_ERR_BAD_ARG;
+  const int ndev = device_count();
+  if (ndev <= 0) return FMC_ERR_NO_DEVICE;
+  int G = ngpus == 0 ? ndev : (ngpus < ndev ? ngpus : ndev);
+  if ((long long)G > nresample) G = nresample > 0 ? (int)nresample : 1;
+  const ModelEntry& m = models()[model];
+  const int P = m.nparam, Q = m.nprop, AL = acc_len(P, Q);
+  const bool keep = params_out || props_out;
+
+  std::vector<int> rcs(G, FMC_OK);
+  std::vector<std::string> errs(G);
+  std::vector<std::vector<double>> accs(G, std::vector<double>(AL, 0.0));
+  auto shard = [&](int g) {
+    // contiguous split of the resample ids
+    const long long lo = nresample * g / G, hi = nresample * (g + 1) / G, cnt = hi - lo;
+    fmc_context* c = nullptr;
+    int rc = cached_context(g, &c);
+    double* zdev = nullptr;
+    do {
+      if (rc != FMC_OK) break;
+      if ((rc = fmc_set_data(c, model, ndata, x, y, err_y)) != FMC_OK) break;
+      if (z_inject && cnt > 0) {
+        if (cudaMalloc(&zdev, sizeof(double) * (size_t)cnt * ndata) != cudaSuccess) {
+          rc = FMC_ERR_ALLOC;
+          break;
+        }
+        if (cudaMemcpyAsync(zdev, z_inject + (size_t)lo * ndata, sizeof(double) * (size_t)cnt * ndata,
+                            cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+          rc = FMC_ERR_CUDA;
+          break;
+        }
+      }
+      fmc_set_accumulator_dev(c, nullptr);
+      if ((rc = fmc_launch(c, params_start, cnt, seed, first_counter + lo, zdev, keep ? 1 : 0)) != FMC_OK) break;
+      rc = fmc_finish(c, nullptr, nullptr, nullptr, nullptr, params_out ? params_out + (size_t)lo * P : nullptr,
+                      (props_out && Q > 0) ? props_out + (size_t)lo * Q : nullptr, nullptr, nullptr, nullptr);
+      if (rc != FMC_OK) break;
+      if (cudaMemcpy(accs[g].data(), c->acc, sizeof(double) * AL, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = FMC_ERR_CUDA;
+    } while (0);
+    if (zdev) cudaFree(zdev);
+    rcs[g] = rc;
+    errs[g] = g_last_cuda_error;
+  };
+  if (G == 1) {
+    shard(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) th.emplace_back(shard, g);
+    for (auto& t : th) t.join();
+  }
+  for (int g = 0; g < G; ++g)
+    if (rcs[g] != FMC_OK) {
+      g_last_cuda_error = errs[g];
+      return rcs[g];
+    }
+  // combine the per-GPU accumulator blocks (what an all-reduce does across ranks)
+  std::vector<double> acc(AL, 0.0);
+  for (int g = 0; g < G; ++g)
+    for (int i = 0; i < AL; ++i) acc[i] += accs[g][i];
+  return fmc_decode_accumulator(model, params_start, acc.data(), sum_p, sum_p2, sum_prop, sum_prop2, nullptr,
+                                rc_count, totals);
+}
+
+int fmc_fit_once(int model, int ndata, const double* x, const double* y, const double* err_y, double* params,
+                 int* rc2) {
+  if (!params) return FMC_ERR_BAD_ARG;
+  if (model < 0 || model >= fmc_model_count()) return FMC_ERR_BAD_MODEL;
+  if (device_count() <= 0) return FMC_ERR_NO_DEVICE;
+  fmc_context* c = nullptr;
+  int rc = cached_context(0, &c);
+  if (rc != FMC_OK) return rc;
+  if ((rc = fmc_set_data(c, model, ndata, x, y, err_y)) != FMC_OK) return rc;
+  // offset_data(.FALSE.): a single "resample" with all offsets zero
+  double* zdev = nullptr;
+  FMC_CUDA(cudaMalloc(&zdev, sizeof(double) * ndata));
+  FMC_CUDA(cudaMemsetAsync(zdev, 0, sizeof(double) * ndata, c->stream));
+  fmc_set_accumulator_dev(c, nullptr);
+  rc = fmc_launch(c, params, 1, 0ULL, 0, zdev, 1);
+  const int P = models()[model].nparam;
+  std::vector<double> pout(P);
+  int cnt[10];
+  if (rc == FMC_OK) rc = fmc_finish(c, nullptr, nullptr, nullptr, nullptr, pout.data(), nullptr, cnt, nullptr, nullptr);
+  cudaFree(zdev);
+  if (rc != FMC_OK) return rc;
+  for (int i = 0; i < P; ++i) params[i] = pout[i];
+  if (rc2) {
+    rc2[0] = cnt[0];
+    rc2[1] = cnt[5];
+  }
+  return FMC_OK;
+}
+
+int fmc_measure_dfma_peak(int device, int iters, double* tflops, float* ms_out) {
+  if (!tflops || iters < 1) return FMC_ERR_BAD_ARG;
+  if (device_count() <= 0) return FMC_ERR_NO_DEVICE;
+  FMC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FMC_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  double* out = nullptr;
+  FMC_CUDA(cudaMalloc(&out, sizeof(double) * threads * blocks));
+  cudaEvent_t e0, e1;
+  FMC_CUDA(cudaEventCreate(&e0));
+  FMC_CUDA(cudaEventCreate(&e1));
+  dfma_peak_kernel<<<blocks, threads>>>(out, iters / 8 + 1, 0.999999, 1e-6);  // warm-up
+  FMC_CUDA(cudaEventRecord(e0));
+  dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-6);
+  FMC_CUDA(cudaEventRecord(e1));
+  FMC_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  FMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  if (ms_out) *ms_out = ms;
+  return FMC_OK;
+}
+
+int fmc_generate_offsets(unsigned long long seed, long long first_counter, long long nresample, int ndata,
+                         double* z_out) {
+  if (!z_out || nresample < 0 || ndata < 1) return FMC_ERR_BAD_ARG;
+  if (device_count() <= 0) return FMC_ERR_NO_DEVICE;
+  if (nresample == 0) return FMC_OK;
+  fmc_context* c = nullptr;
+  int rc = cached_context(0, &c);
+  if (rc != FMC_OK) return rc;
+  double* zdev = nullptr;
+  FMC_CUDA(cudaMalloc(&zdev, sizeof(double) * (size_t)nresample * ndata));
+  generate_offsets_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(seed, first_counter, nresample, ndata, zdev);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(z_out, zdev, sizeof(double) * (size_t)nresample * ndata, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(zdev);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = std::string("generate_offsets: ") + cudaGetErrorString(e);
+    return FMC_ERR_CUDA;
+  }
+  return FMC_OK;
+}
+
+}  // extern "C"

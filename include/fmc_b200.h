@@ -1,0 +1,143 @@
+/* fmc_b200 -- C ABI of the B200-native bootstrap-fitting engine (libfmc_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of ndd21/Fitter_MC: the Monte-Carlo
+ * (parametric bootstrap) loop of `monte_carlo_fit_data`, bootstrap.f90:297-330, i.e. per
+ * resample  offset_data(.TRUE.) -> fit_data (two nl2sno calls) -> derived_properties ->
+ * accumulation of sum p, sum p^2, sum prop, sum prop^2.  The reference has no FFI for this
+ * path (its plug-in surface is source-level, bootstrap.f90:365-407); these entry points are
+ * what a Fortran `INTERFACE ... BIND(C)` block, a C++ driver or ctypes binds instead.  See
+ * INTEGRATION.md for the Fortran binding and the five-line change to bootstrap.f90.
+ *
+ * Conventions
+ *  - plain pointers and sizes; every array is caller-owned, contiguous, host memory unless
+ *    the name says `_dev`; the library keeps nothing after a call returns except inside an
+ *    fmc_context the caller created.
+ *  - return value 0 = success, negative = error (fmc_strerror).  The Fortran shim turns a
+ *    non-zero code into errstop('MONTE_CARLO_FIT_DATA', fmc_strerror(rc)), the reference's
+ *    error convention (utils.f90:26-37).  Solver non-convergence is NOT an error: the
+ *    reference never inspects nl2sno's return code (bootstrap.f90:215-226) and averages
+ *    every fit; so does this library (the codes are returned as a histogram instead).
+ *  - there is no CPU fallback: every compute entry point fails with FMC_ERR_NO_DEVICE
+ *    when no CUDA device is usable.
+ *  - not re-entrant per context; use one context per host thread / per GPU.
+ *  - results are a deterministic function of (data, params_start, seed, global resample id):
+ *    every resample draws its Gaussian offsets from a counter-based generator keyed by its
+ *    global id, so any split of [first_counter, first_counter+nresample) over launches,
+ *    GPUs or ranks gives the same fits (sums agree up to summation order).
+ */
+#ifndef FMC_B200_H
+#define FMC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMC_OK 0
+#define FMC_ERR_NO_DEVICE (-1)   /* no usable CUDA device / driver */
+#define FMC_ERR_CUDA (-2)        /* a CUDA call failed; fmc_last_cuda_error() has the text */
+#define FMC_ERR_BAD_MODEL (-3)   /* model id out of range */
+#define FMC_ERR_BAD_ARG (-4)     /* null pointer, ndata < nparam, nresample < 0, err_y <= 0 ... */
+#define FMC_ERR_NO_DATA (-5)     /* fmc_launch before fmc_set_data */
+#define FMC_ERR_STATE (-6)       /* fmc_finish without a launch in flight */
+#define FMC_ERR_ALLOC (-7)       /* host or device allocation failed */
+
+#define FMC_MAX_PARAM 16
+#define FMC_DEFAULT_SEED 31415ULL /* the reference's seed, utils.f90:7 */
+
+typedef struct fmc_context fmc_context; /* opaque: device buffers + stream of one GPU */
+
+/* ---------------------------------------------------------------- model plug-in trio
+ * Replaces SUBROUTINE initialise_model / FUNCTION model_y / SUBROUTINE derived_properties
+ * (bootstrap.f90:365-387, 390-396, 399-407).  The routines themselves live in
+ * fitter_mc_b200/csrc/models/model_user.cuh (model id 0; edit and rebuild, as with the
+ * reference) and are compiled into the kernels; these are their host-callable images.
+ * param_name / prop_name are the reference's CHARACTER(2) names, blank padded, NUL added. */
+int fmc_model_count(void);
+int fmc_initialise_model(int model, int* nparam, int* nprop, double* params_init,
+                         char (*param_name)[3], char (*prop_name)[3], char* model_name32);
+double fmc_model_y(int model, const double* params, double x);
+int fmc_derived_properties(int model, const double* params, double* props);
+
+/* ---------------------------------------------------------------- one-shot entry points */
+
+/* The Monte-Carlo loop, bootstrap.f90:297-330 (zero sums -> loop -> the caller applies
+ * 328-341).  Resamples [first_counter, first_counter + nresample) are split contiguously
+ * over `ngpus` devices (0 = all visible), one host thread per GPU; the per-GPU accumulators
+ * are combined on the host.  Inputs: x ascending as after sort_data (bootstrap.f90:155-194),
+ * err_y > 0 (bootstrap.f90:134-138).
+ *   sum_p[nparam], sum_p2[nparam], sum_prop[nprop], sum_prop2[nprop]  raw sums, so that the
+ *       caller's lines 328-341 apply unchanged (computed from compensated shifted sums).
+ *   z_inject     NULL, or [nresample][ndata] offsets in units of err_y used INSTEAD of the
+ *                generator (parity tests feed the same resamples to the oracle).
+ *   params_out   NULL or [nresample][nparam]; props_out NULL or [nresample][nprop] (what the
+ *                reference writes to histogram_<prop>.dat, bootstrap.f90:319-325).
+ *   rc_count     NULL or [16]: histogram of nl2sno's return code iv(1) of the second call
+ *                (3 x-conv, 4 rel-f, 5 both, 6 abs-f, 7 singular, 8 false, 9/10 limits).
+ *   totals       NULL or [4]: sum over fits of nfcall, ngcall, niter, passes over the data. */
+int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, const double* err_y,
+                      const double* params_start, long long nresample, unsigned long long seed,
+                      long long first_counter, int ngpus, const double* z_inject,
+                      double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,
+                      double* params_out, double* props_out, long long* rc_count, long long* totals);
+
+/* The un-resampled fit of bootstrap.f90:288-291: offset_data(.FALSE.); fit_data(params).
+ * params is in/out; rc2[2] (may be NULL) receives nl2sno's return code of both calls. */
+int fmc_fit_once(int model, int ndata, const double* x, const double* y, const double* err_y,
+                 double* params, int* rc2);
+
+/* The Gaussian offsets (in units of err_y) the engine uses for resamples
+ * [first_counter, first_counter+nresample): z_out[nresample][ndata].  Replaces
+ * `rang(ndata, offset)` (utils.f90:345-364) as a reproducible per-sample generator. */
+int fmc_generate_offsets(unsigned long long seed, long long first_counter, long long nresample,
+                         int ndata, double* z_out);
+
+/* ---------------------------------------------------------------- context API (one GPU)
+ * For callers that keep data resident, overlap transfers, shard over ranks or combine
+ * accumulators with their own collective (bench.py, the multi-GPU path). */
+int fmc_create(fmc_context** ctx, int device);
+int fmc_destroy(fmc_context* ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own. */
+int fmc_set_stream(fmc_context* ctx, void* cuda_stream);
+/* Copy the data to the GPU (also precomputes 1/err_y, bootstrap.f90:140). */
+int fmc_set_data(fmc_context* ctx, int model, int ndata, const double* x, const double* y,
+                 const double* err_y);
+/* Accumulate into a caller-owned device buffer of fmc_accumulator_len() doubles (e.g. a
+ * torch tensor that is then all-reduced with NCCL).  NULL = the context's own buffer. */
+int fmc_set_accumulator_dev(fmc_context* ctx, double* acc_dev);
+int fmc_accumulator_len(const fmc_context* ctx);
+/* Enqueue: zero the accumulator, run the fit kernel for `nresample` resamples.  Asynchronous.
+ * z_inject_dev: NULL or DEVICE pointer [nresample][ndata].  keep_per_resample != 0 keeps
+ * per-resample params/props/counters on the device for fmc_finish. */
+int fmc_launch(fmc_context* ctx, const double* params_start, long long nresample,
+               unsigned long long seed, long long first_counter, const double* z_inject_dev,
+               int keep_per_resample);
+/* Wait for the launch and read back.  Any output pointer may be NULL.
+ * counters_out [nresample][10]: per nl2sno call (rc, nfcall, ngcall, niter, passes). */
+int fmc_finish(fmc_context* ctx, double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,
+               double* params_out, double* props_out, int* counters_out, long long* rc_count,
+               long long* totals);
+/* Turn an accumulator block (host copy, possibly summed over GPUs) into the raw sums. */
+int fmc_decode_accumulator(int model, const double* params_start, const double* acc_host,
+                           double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,
+                           long long* nfit, long long* rc_count, long long* totals);
+/* Device time of the last fit kernel (CUDA events on the launching stream), milliseconds. */
+float fmc_last_kernel_ms(fmc_context* ctx);
+/* Grid geometry chosen for the last launch: blocks, threads per block, blocks per SM, SMs. */
+int fmc_last_launch_geometry(const fmc_context* ctx, int* out4);
+
+/* bootstrap.f90:328-341: mean and Bessel-corrected standard deviation from the raw sums. */
+void fmc_finalise_moments(int k, long long nresample, const double* sum, const double* sum2,
+                          double* mean, double* err);
+
+/* FP64 roofline denominator: runs register-resident DFMA chains (iters x 128 FMAs per thread,
+ * 8 independent chains, every SM full) and returns the achieved TFLOP/s (FMA = 2 flops). */
+int fmc_measure_dfma_peak(int device, int iters, double* tflops, float* ms_out);
+
+const char* fmc_strerror(int code);
+const char* fmc_last_cuda_error(void);
+const char* fmc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMC_B200_H */

@@ -1,0 +1,142 @@
+// Host build of the PRODUCT's solver logic (fitter_mc_b200/csrc/nl2_solver.cuh,
+// pass_eval.cuh, rng.cuh, models) for unit tests in a container without a GPU.
+//
+// This is a test harness: it drives exactly the same per-fit state machine and per-row
+// pass code the CUDA kernel uses, one fit after another on the CPU, so that its logic can
+// be compared with the oracle here before a GPU run.  It is compiled only by the tests; the
+// shipped library has no CPU path.
+#include <cstring>
+#include <vector>
+
+#include "../../fitter_mc_b200/csrc/models/model_user.cuh"
+#include "../../fitter_mc_b200/csrc/models/models_bench.cuh"
+#include "../../fitter_mc_b200/csrc/nl2_solver.cuh"
+#include "../../fitter_mc_b200/csrc/pass_eval.cuh"
+#include "../../fitter_mc_b200/csrc/rng.cuh"
+
+using namespace fmc;
+
+namespace {
+
+template <class M>
+void run_pass(Nl2<M::NPARAM>& s, int n, const double* x, const double* yfit, const double* rerr) {
+  constexpr int P = M::NPARAM;
+  PassPoint<P> a, b;
+  a.set(s.x, s.hA);
+  b.set(s.x0, s.hJ);
+  PassAcc<P> acc;
+  acc.zero();
+  for (int i = 0; i < n; ++i) {
+    if (s.need_b)
+      row_accumulate<M, true>(a, b, x[i], yfit[i], rerr[i], acc);
+    else
+      row_accumulate<M, false>(a, b, x[i], yfit[i], rerr[i], acc);
+  }
+  s.res_f = acc.f;
+  for (int i = 0; i < P; ++i) {
+    s.res_g[i] = acc.g[i];
+    s.res_lky[i] = acc.lky[i];
+  }
+  for (int i = 0; i < PassAcc<P>::PP; ++i) s.res_G[i] = acc.G[i];
+}
+
+// counters[pass][0..3] = rc, nfcall, ngcall, niter ; counters[pass][4] = passes over the data
+template <class M>
+int fit_one(int n, const double* x, const double* yfit, const double* err, double* params,
+            int* counters) {
+  constexpr int P = M::NPARAM;
+  std::vector<double> rerr(n);
+  for (int i = 0; i < n; ++i) rerr[i] = 1.0 / err[i];
+  Nl2<P> s;
+  std::memset(&s, 0, sizeof(s));
+  s.reset_fit();
+  for (int pass = 0; pass < 2; ++pass) {
+    s.begin(params);
+    int npass = 0;
+    for (;;) {
+      run_pass<M>(s, n, x, yfit, rerr.data());
+      ++npass;
+      if (!s.resume()) break;
+    }
+    for (int i = 0; i < P; ++i) params[i] = s.x[i];
+    if (counters) {
+      int* c = counters + 5 * pass;
+      c[0] = s.rc;
+      c[1] = s.nfcall;
+      c[2] = s.ngcall;
+      c[3] = s.niter;
+      c[4] = npass;
+    }
+  }
+  return 0;
+}
+
+template <class M>
+int bootstrap(int n, const double* x, const double* y, const double* err, const double* start,
+              long long nres, const double* z, unsigned long long seed, long long first,
+              double* params_out, double* props_out, int* counters_out) {
+  constexpr int P = M::NPARAM, Q = M::NPROP;
+  std::vector<double> yfit(n), p(P);
+  for (long long r = 0; r < nres; ++r) {
+    if (z) {
+      for (int i = 0; i < n; ++i) yfit[i] = fma(z[(size_t)r * n + i], err[i], y[i]);
+    } else {
+      for (int i = 0; i < n; i += 4) {
+        float zz[4];
+        normals4(seed, (uint64_t)(first + r), (uint32_t)(i / 4), zz);
+        for (int m = 0; m < 4 && i + m < n; ++m) yfit[i + m] = fma((double)zz[m], err[i + m], y[i + m]);
+      }
+    }
+    for (int i = 0; i < P; ++i) p[i] = start[i];
+    fit_one<M>(n, x, yfit.data(), err, p.data(), counters_out ? counters_out + 10 * r : nullptr);
+    std::memcpy(params_out + (size_t)r * P, p.data(), sizeof(double) * P);
+    if (props_out) M::derived_properties(p.data(), props_out + (size_t)r * Q);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emul_fit(int model, int n, const double* x, const double* yfit, const double* err, double* params,
+             int* counters) {
+  switch (model) {
+    case 0: return fit_one<ModelUser>(n, x, yfit, err, params, counters);
+    case 1: return fit_one<ModelTest4>(n, x, yfit, err, params, counters);
+    case 2: return fit_one<ModelPeaks10>(n, x, yfit, err, params, counters);
+    case 3: return fit_one<ModelStiff4>(n, x, yfit, err, params, counters);
+  }
+  return -1;
+}
+
+int emul_bootstrap(int model, int n, const double* x, const double* y, const double* err,
+                   const double* start, long long nres, const double* z, unsigned long long seed,
+                   long long first, double* params_out, double* props_out, int* counters_out) {
+  switch (model) {
+    case 0: return bootstrap<ModelUser>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
+    case 1: return bootstrap<ModelTest4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
+    case 2: return bootstrap<ModelPeaks10>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
+    case 3: return bootstrap<ModelStiff4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
+  }
+  return -1;
+}
+
+void emul_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+  U4 c{c0, c1, c2, c3};
+  U4 o = philox4x32_10(c, k0, k1);
+  out[0] = o.x;
+  out[1] = o.y;
+  out[2] = o.z;
+  out[3] = o.w;
+}
+
+void emul_normals(unsigned long long seed, long long id, int n, double* z) {
+  for (int i = 0; i < n; i += 4) {
+    float zz[4];
+    normals4(seed, (uint64_t)id, (uint32_t)(i / 4), zz);
+    for (int m = 0; m < 4 && i + m < n; ++m) z[i + m] = (double)zz[m];
+  }
+}
+
+}  // extern "C"
