@@ -67,6 +67,7 @@ def lib():
     L.fmc_accumulator_len.argtypes = [C.c_void_p]
     L.fmc_launch.argtypes = [C.c_void_p, _dp, C.c_longlong, C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_int]
     L.fmc_finish.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _lp, _lp]
+    L.fmc_wait.argtypes = [C.c_void_p]
     L.fmc_decode_accumulator.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _lp, _lp, _lp]
     L.fmc_last_kernel_ms.restype = C.c_float
     L.fmc_last_kernel_ms.argtypes = [C.c_void_p]
@@ -264,6 +265,9 @@ class Context:
                                 rcc.ctypes.data_as(_lp), tot.ctypes.data_as(_lp)), "fmc_finish")
         return dict(sum_p=s[0], sum_p2=s[1], sum_prop=s[2][:q], sum_prop2=s[3][:q], params=pout,
                     props=None if qout is None else qout[:, :q], counters=cout, rc_count=rcc, totals=tot)
+
+    def wait(self):
+        _check(lib().fmc_wait(self._h), "fmc_wait")
 
     def kernel_ms(self):
         return float(lib().fmc_last_kernel_ms(self._h))

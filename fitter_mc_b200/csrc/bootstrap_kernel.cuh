@@ -95,7 +95,6 @@ template <class M, bool INJECT, bool SMEM>
 __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) bootstrap_fit_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int Q = M::NPROP;
-  constexpr int PP = P * (P + 1) / 2;
   constexpr int NM = 2 * (P + Q);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[FMC_THREADS / 32];
@@ -158,14 +157,7 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) bootstrap_fit_ker
         pass_loop<M, INJECT, true>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
       else
         pass_loop<M, INJECT, false>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
-      s.res_f = acc.f;
-#pragma unroll
-      for (int i = 0; i < P; ++i) {
-        s.res_g[i] = acc.g[i];
-        s.res_lky[i] = acc.lky[i];
-      }
-#pragma unroll
-      for (int i = 0; i < PP; ++i) s.res_G[i] = acc.G[i];
+      pass_finish<P>(acc, s);
       ++fit_passes;
       ++n_pass;
 

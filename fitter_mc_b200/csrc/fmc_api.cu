@@ -96,7 +96,7 @@ struct fmc_context {
   double* params_out_dev = nullptr;
   double* props_out_dev = nullptr;
   int* counters_dev = nullptr;
-  long long out_cap = 0;
+  long long out_cap_p = 0, out_cap_q = 0, out_cap_c = 0;  // capacities in elements
   long long inflight = -1;
   bool keep = false;
   double start[16] = {0};
@@ -280,17 +280,30 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   if (c->inflight >= 0) FMC_CUDA(cudaStreamSynchronize(c->stream));
   const int P = m.nparam, Q = m.nprop;
   c->keep = keep_per_resample != 0;
-  if (c->keep && nresample > c->out_cap) {
-    cudaFree(c->params_out_dev);
-    cudaFree(c->props_out_dev);
-    cudaFree(c->counters_dev);
-    c->params_out_dev = c->props_out_dev = nullptr;
-    c->counters_dev = nullptr;
-    c->out_cap = 0;
-    FMC_CUDA(cudaMalloc(&c->params_out_dev, sizeof(double) * P * nresample));
-    FMC_CUDA(cudaMalloc(&c->props_out_dev, sizeof(double) * (Q > 0 ? Q : 1) * nresample));
-    FMC_CUDA(cudaMalloc(&c->counters_dev, sizeof(int) * 10 * nresample));
-    c->out_cap = nresample;
+  if (c->keep) {
+    const long long need_p = (long long)P * nresample, need_q = (long long)(Q > 0 ? Q : 1) * nresample,
+                    need_c = 10LL * nresample;
+    if (need_p > c->out_cap_p) {
+      cudaFree(c->params_out_dev);
+      c->params_out_dev = nullptr;
+      c->out_cap_p = 0;
+      FMC_CUDA(cudaMalloc(&c->params_out_dev, sizeof(double) * need_p));
+      c->out_cap_p = need_p;
+    }
+    if (need_q > c->out_cap_q) {
+      cudaFree(c->props_out_dev);
+      c->props_out_dev = nullptr;
+      c->out_cap_q = 0;
+      FMC_CUDA(cudaMalloc(&c->props_out_dev, sizeof(double) * need_q));
+      c->out_cap_q = need_q;
+    }
+    if (need_c > c->out_cap_c) {
+      cudaFree(c->counters_dev);
+      c->counters_dev = nullptr;
+      c->out_cap_c = 0;
+      FMC_CUDA(cudaMalloc(&c->counters_dev, sizeof(int) * need_c));
+      c->out_cap_c = need_c;
+    }
   }
   KernelArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -406,6 +419,15 @@ int fmc_finish(fmc_context* c, double* sum_p, double* sum_p2, double* sum_prop, 
     g_last_cuda_error = "kernel finished " + std::to_string(nfit) + " of " + std::to_string(nres) + " fits";
     return FMC_ERR_CUDA;
   }
+  return FMC_OK;
+}
+
+int fmc_wait(fmc_context* c) {
+  if (!c) return FMC_ERR_BAD_ARG;
+  if (c->inflight < 0) return FMC_ERR_STATE;
+  FMC_CUDA(cudaSetDevice(c->device));
+  FMC_CUDA(cudaStreamSynchronize(c->stream));
+  c->inflight = -1;
   return FMC_OK;
 }
 

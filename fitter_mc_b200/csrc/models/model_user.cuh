@@ -13,6 +13,7 @@
 // As shipped it is the reference's own model: y = a + b*exp(-al*x), property ab = a + b.
 #pragma once
 #include "../fmc_common.cuh"
+#include "../fast_math.cuh"
 
 namespace fmc {
 

@@ -3,6 +3,7 @@
 // through the C ABI; id 0 is always the user's model.
 #pragma once
 #include "../fmc_common.cuh"
+#include "../fast_math.cuh"
 
 namespace fmc {
 

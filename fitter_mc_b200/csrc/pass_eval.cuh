@@ -16,16 +16,13 @@ namespace fmc {
 // An evaluation point with its finite-difference steps, held in registers for a whole pass.
 template <int P>
 struct PassPoint {
-  double x[P];     // parameters
-  double xh[P];    // x[k] + h[k]: the k-th perturbed coordinate (toms573.f90:718)
-  double hinv[P];  // 1 / h[k]   (the reference divides by h; one rounding of difference, far
-                   //             below the 1e-8 truncation error of the forward difference)
+  double x[P];   // parameters
+  double xh[P];  // x[k] + h[k]: the k-th perturbed coordinate (toms573.f90:718)
   FMC_HD FMC_INLINE void set(const double* xs, const double* h) {
 #pragma unroll
     for (int kk = 0; kk < P; ++kk) {
       x[kk] = xs[kk];
       xh[kk] = xs[kk] + h[kk];
-      hinv[kk] = 1.0 / h[kk];
     }
   }
 };
@@ -49,12 +46,16 @@ struct PassAcc {
   }
 };
 
-// Residual and Jacobian row at `pt` for the data point (xi, yfit, 1/err).  Because the
+// Residual and UNSCALED Jacobian row at `pt` for the data point (xi, yfit, 1/err):
+// D[k] = r(x + h_k e_k) - r(x).  The division by h_k of toms573.f90:729-732 is a constant
+// factor per column, so it is applied once per pass to the p x p sums (pass_finish) instead
+// of n times per column -- same value up to one rounding per term, 2p fewer FP64 ops per row.
+// Because the
 // model is inlined p+1 times with all but one coordinate identical, common subexpressions
 // (e.g. exp(-al*x) of the default model for every column except al's) are evaluated once.
 template <class M>
 FMC_HD FMC_INLINE void row_eval(const PassPoint<M::NPARAM>& pt, double xi, double yfit, double rerr,
-                                double& r0, double (&J)[M::NPARAM]) {
+                                double& r0, double (&D)[M::NPARAM]) {
   constexpr int P = M::NPARAM;
   r0 = (yfit - M::model_y(pt.x, xi)) * rerr;
 #pragma unroll
@@ -63,7 +64,7 @@ FMC_HD FMC_INLINE void row_eval(const PassPoint<M::NPARAM>& pt, double xi, doubl
 #pragma unroll
     for (int m = 0; m < P; ++m) xs[m] = (m == kk) ? pt.xh[m] : pt.x[m];
     const double rk = (yfit - M::model_y(xs, xi)) * rerr;
-    J[kk] = (rk - r0) * pt.hinv[kk];
+    D[kk] = rk - r0;
   }
 }
 
@@ -90,6 +91,29 @@ FMC_HD FMC_INLINE void row_accumulate(const PassPoint<M::NPARAM>& a, const PassP
     row_eval<M>(b, xi, yfit, rerr, rb, Jb);
 #pragma unroll
     for (int i = 0; i < P; ++i) acc.lky[i] = fma(Jb[i], ra, acc.lky[i]);
+  }
+}
+
+// Apply the 1/h_k column factors to the sums of a finished pass and hand them to the solver.
+template <int P, class Solver>
+FMC_HD FMC_INLINE void pass_finish(const PassAcc<P>& acc, Solver& s) {
+  double ia[P], ib[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    ia[i] = 1.0 / s.hA[i];
+    ib[i] = 1.0 / s.hJ[i];
+  }
+  s.res_f = acc.f;
+  int m = 0;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    s.res_g[i] = acc.g[i] * ia[i];
+    s.res_lky[i] = acc.lky[i] * ib[i];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      s.res_G[m] = acc.G[m] * (ia[i] * ia[j]);
+      ++m;
+    }
   }
 }
 

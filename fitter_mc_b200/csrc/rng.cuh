@@ -11,6 +11,8 @@
 // issue slots the FP64 pipe leaves free, so regenerating z in every pass over the data costs
 // no FP64 throughput and no memory.
 #pragma once
+#include <cstring>
+
 #include "fmc_common.cuh"
 
 namespace fmc {
@@ -50,9 +52,41 @@ FMC_HD FMC_INLINE U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 }
 
 // Box-Muller on two 32-bit words: u in (0,1], angle = 2*pi*v with v in [0,1).
+// Branch-free: u is always a normal positive float (>= 2^-33), so ln(u) needs no special
+// cases; ln(u) = e*ln2 + ln(m), m in [sqrt(1/2), sqrt(2)), ln(m) by the atanh series in
+// s = (m-1)/(m+1) (|s| < 0.172, truncation error < 2e-9 relative).
+FMC_HD FMC_INLINE float ln_pos_normal(float u) {
+#if defined(__CUDA_ARCH__)
+  int bits = __float_as_int(u);
+#else
+  int bits;
+  memcpy(&bits, &u, 4);
+#endif
+  int e = ((bits - 0x3f3504f3) >> 23);           // exponent such that m = u * 2^-e is in [0.7071, 1.4142)
+  int mb = bits - (e << 23);
+#if defined(__CUDA_ARCH__)
+  float m = __int_as_float(mb);
+  const float s = __fdividef(m - 1.0f, m + 1.0f);
+#else
+  float m;
+  memcpy(&m, &mb, 4);
+  const float s = (m - 1.0f) / (m + 1.0f);
+#endif
+  const float s2 = s * s;
+  float p = fmaf(s2, 0.2857142857f, 0.4f);        // 2/7, 2/5
+  p = fmaf(p, s2, 0.6666666667f);                 // 2/3
+  p = fmaf(p, s2, 2.0f);
+  return fmaf((float)e, 0.6931471806f, p * s);
+}
+
 FMC_HD FMC_INLINE void normal_pair(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // 2^-32
-  const float r = sqrtf(-2.0f * logf(u));
+  const float t = -2.0f * ln_pos_normal(u);                       // >= 0 (u <= 1)
+#if defined(__CUDA_ARCH__)
+  const float r = (t > 0.0f) ? t * rsqrtf(t) : 0.0f;
+#else
+  const float r = (t > 0.0f) ? sqrtf(t) : 0.0f;
+#endif
   const float v2 = (float)b * 4.6566128730773926e-10f;            // 2 * b * 2^-32
   float s, c;
 #if defined(__CUDA_ARCH__)

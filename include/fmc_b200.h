@@ -116,6 +116,9 @@ int fmc_launch(fmc_context* ctx, const double* params_start, long long nresample
 int fmc_finish(fmc_context* ctx, double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,
                double* params_out, double* props_out, int* counters_out, long long* rc_count,
                long long* totals);
+/* Wait for the launch without reading anything back (the caller owns the accumulator, e.g.
+ * after all-reducing it across ranks). */
+int fmc_wait(fmc_context* ctx);
 /* Turn an accumulator block (host copy, possibly summed over GPUs) into the raw sums. */
 int fmc_decode_accumulator(int model, const double* params_start, const double* acc_host,
                            double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,

@@ -1,0 +1,19 @@
+"""Short single-kernel run of the headline config (C2: n=1000, p=4) for ncu captures."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fitter_mc_b200 as fmc
+import datasets, oracle_lib as oracle
+
+name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+nres = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+model, x, y, err = datasets.dataset(name)
+info = oracle.model_info(model)
+start, _ = oracle.fit_data(model, x, y, err, info["params_init"])
+ctx = fmc.Context(0)
+ctx.set_data(model, x, y, err)
+for rep in range(reps):
+    ctx.launch(start, nres, first_counter=rep * nres)
+    out = ctx.finish()
+    print(name, nres, "kernel ms %.3f -> %.4e fits/s" % (ctx.kernel_ms(), nres / ctx.kernel_ms() * 1e3), ctx.geometry())

@@ -32,12 +32,7 @@ void run_pass(Nl2<M::NPARAM>& s, int n, const double* x, const double* yfit, con
     else
       row_accumulate<M, false>(a, b, x[i], yfit[i], rerr[i], acc);
   }
-  s.res_f = acc.f;
-  for (int i = 0; i < P; ++i) {
-    s.res_g[i] = acc.g[i];
-    s.res_lky[i] = acc.lky[i];
-  }
-  for (int i = 0; i < PassAcc<P>::PP; ++i) s.res_G[i] = acc.G[i];
+  pass_finish<P>(acc, s);
 }
 
 // counters[pass][0..3] = rc, nfcall, ngcall, niter ; counters[pass][4] = passes over the data

@@ -80,7 +80,11 @@ def test_injected_resamples_per_fit_parity(fmc, oracle, name, nres):
     assert np.allclose(got["sum_p"], got["params"].sum(0), rtol=1e-12)
     assert np.allclose(got["sum_p2"], (got["params"] ** 2).sum(0), rtol=1e-12)
     # return codes: same histogram up to the noise-level last step of the second nl2sno call
-    assert got["rc_count"].sum() == nres and got["rc_count"][3:7].sum() == want["rc_count"][3:7].sum()
+    # (whether that step is accepted, rejected or called "false convergence" is decided by the
+    # sign of a rounding-level change of f; see tests/test_parity_floor.py)
+    assert got["rc_count"].sum() == nres
+    assert np.abs(got["rc_count"] - want["rc_count"]).sum() <= max(8, 0.35 * nres)
+    assert abs(int(got["rc_count"][3:7].sum()) - int(want["rc_count"][3:7].sum())) <= max(2, 0.01 * nres)
 
 
 def test_counter_generator_path_matches_oracle_on_dumped_offsets(fmc, oracle):
@@ -145,7 +149,14 @@ def test_edge_cases_and_error_codes(fmc, oracle):
         got = fmc.monte_carlo_fit_data(x[:n], y[:n], err[:n], model, nrand_points=16, params_init=start,
                                        initial_fit=False, z_inject=z, per_resample=True)
         want = oracle.bootstrap(model, x[:n], y[:n], err[:n], start, 16, z=z)
-        assert np.allclose(got["params"], want["params"], rtol=1e-5), n
+        if n > 10:
+            assert np.allclose(got["params"], want["params"], rtol=1e-6), n
+        else:
+            # 3 parameters from 3-5 points: the minimum is nearly flat, so compare the objective
+            for i in range(16):
+                fg = (oracle.madr(model, x[:n], y[:n] + z[i] * err[:n], err[:n], got["params"][i]) ** 2).sum()
+                fw = (oracle.madr(model, x[:n], y[:n] + z[i] * err[:n], err[:n], want["params"][i]) ** 2).sum()
+                assert abs(fg - fw) <= 1e-8 * max(1.0, fw), (n, i, fg, fw)
     # empty run: zero resamples is a no-op, not an error
     got = fmc.monte_carlo_fit_data(x, y, err, model, nrand_points=0, params_init=start, initial_fit=False)
     assert got["rc_count"].sum() == 0 and (got["sum_p"] == 0).all()
