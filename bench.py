@@ -272,7 +272,7 @@ def main():
                        "wall_s_timed_region": t_wall},
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(8 * (3 * NDATA + p)),
                     "d2h_bytes_per_step": int(8 * ctx.accumulator_len())},
-            "gpu_launches": args.steps * world,
+            "gpu_launches": 4 * args.steps * world,  # init_pass + iterate kernels for each of fit_data's two nl2sno calls
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops, "traffic": None,

@@ -1,20 +1,23 @@
-// The bootstrap hot loop as ONE persistent CUDA kernel for sm_100a.
+// The bootstrap hot loop as a short pipeline of CUDA kernels for sm_100a.
 //
 // Replaces bootstrap.f90:309-327 (the !$OMP PARALLEL DO over nrand_points with its
 // REDUCTION(+) and two CRITICAL sections) and everything it calls.
 //
 // Mapping (DESIGN.md has the measurements behind these choices):
-//  * one fit per THREAD.  A thread owns one resample at a time and runs its NL2SOL state
-//    machine (nl2_solver.cuh); when the fit ends it adds the result to its private moment
-//    sums and takes the next resample id from a global counter.  Lanes of a warp are thus at
-//    different iterations of different fits, but all of them always execute the same thing
-//    next -- one streaming pass over the n data points -- so the warp never waits for its
-//    slowest fit ("convergence mask + compaction" by refill).
-//  * the data points (x, y, err, 1/err) sit in shared memory, read by broadcast (every lane
-//    reads the same row); per-fit state is registers + thread-local memory; nothing of length
-//    n is ever stored per fit.  HBM traffic is O(outputs).
-//  * the Gaussian offsets are regenerated from the counter-based generator in every pass
-//    (INT32/FP32/SFU work that issues in the slots the FP64 pipe leaves free).
+//  * one fit per THREAD; nothing of length n is ever stored per fit.  The data points
+//    (x, y, err, 1/err) sit in shared memory and are read by broadcast (every lane reads the
+//    same row); per-fit solver state is registers + thread-local memory; the Gaussian offsets
+//    are regenerated from the counter-based generator in every pass (INT32/FP32/SFU work that
+//    issues in the slots the FP64 pipe leaves free).  HBM traffic is O(outputs) plus ~0.4 KB
+//    of pipeline state per fit.
+//  * fit_data's two nl2sno calls (bootstrap.f90:219-225) become four launches per chunk of
+//    resamples:   init_pass(call 0) -> iterate(call 0) -> init_pass(call 1) -> iterate(call 1).
+//    init_pass is the first residual+Jacobian evaluation of a call: identical work for every
+//    fit, so it runs as a perfectly uniform kernel.  iterate runs the NL2SOL state machine
+//    (nl2_solver.cuh) with REFILL: a thread whose fit ends takes the next one from a shared
+//    counter, so lanes of a warp are at different iterations of different fits but always
+//    execute the same thing next -- one trial pass over the n data points -- and a warp never
+//    waits for its slowest fit ("convergence mask + compaction").
 //  * per-thread compensated (Kahan) sums of shifted values -> warp shuffle -> block ->
 //    one atomicAdd per block into the device accumulator that the caller all-reduces.
 #pragma once
@@ -28,10 +31,16 @@
 namespace fmc {
 
 #ifndef FMC_THREADS
-#define FMC_THREADS 128
+#define FMC_THREADS 256
 #endif
 #ifndef FMC_MIN_BLOCKS
-#define FMC_MIN_BLOCKS 3
+#define FMC_MIN_BLOCKS 1
+#endif
+#ifndef FMC_ROWS_PER_ITER
+#define FMC_ROWS_PER_ITER 4  // data points per trip of the pass loop (4 or 2)
+#endif
+#ifndef FMC_PHILOX_ROUNDS
+#define FMC_PHILOX_ROUNDS 10
 #endif
 
 struct __align__(16) RowData {  // one data point, 32 B: two 16-byte broadcast loads
@@ -51,14 +60,21 @@ struct KernelArgs {
   int n_pad;            // multiple of 4
   double start[16];     // params_start: first guess of every fit and shift of the moment sums
   unsigned long long seed;
-  long long first;      // global id of resample 0 of this launch
-  long long nres;       // resamples in this launch
-  const double* z_inject;   // INJECT only: [nres][n] offsets in units of err
-  double* params_out;       // optional [nres][P]
+  long long first;      // global resample id of slot 0 of this chunk
+  long long nres;       // fits in this chunk
+  long long cap;        // stride of the per-fit state arrays below (chunk capacity)
+  int call;             // 0 = first nl2sno call of fit_data, 1 = second (bootstrap.f90:222-225)
+  const double* z_inject;   // INJECT only: [nres][n] offsets in units of err (chunk-local)
+  // per-fit pipeline state, structure-of-arrays [field][slot] so that lanes coalesce
+  double* xbuf;   // [P]       parameters after the first nl2sno call
+  double* init;   // [1+P+PP]  sums of the initial pass: f, g, G (already scaled by 1/h)
+  int* istate;    // [2]       mlstgd, lsvmin LCG state carried from call 0 to call 1
+  int* cnt;       // [10]      per call: rc, nfcall, ngcall, niter, passes
+  double* params_out;       // optional [nres][P]   (chunk-local)
   double* props_out;        // optional [nres][Q]
-  int* counters_out;        // optional [nres][10]: per pass rc, nfcall, ngcall, niter, passes
-  unsigned long long* next_id;  // work counter, zeroed before launch
-  double* acc;              // accumulator block, zeroed before launch
+  int* counters_out;        // optional [nres][10]
+  unsigned long long* next_id;  // work counter of this launch, zeroed beforehand
+  double* acc;              // accumulator block, zeroed before the first chunk
 };
 
 FMC_INLINE __device__ void kahan_add(double& s, double& c, double v) {
@@ -68,12 +84,14 @@ FMC_INLINE __device__ void kahan_add(double& s, double& c, double v) {
   s = t;
 }
 
+// One streaming pass of one fit over the n data points.
 template <class M, bool INJECT, bool WITH_B>
 FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, int n_pad,
                                      unsigned long long seed, unsigned long long id,
                                      const double* __restrict__ zrow,
                                      const PassPoint<M::NPARAM>& pa, const PassPoint<M::NPARAM>& pb,
                                      PassAcc<M::NPARAM>& acc) {
+#if FMC_ROWS_PER_ITER == 4
   for (int i = 0; i < n_pad; i += 4) {
     float z[4];
     if (!INJECT) normals4(seed, id, (uint32_t)(i >> 2), z);
@@ -89,28 +107,92 @@ FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, in
       row_accumulate<M, WITH_B>(pa, pb, rd.x, yfit, rd.rerr, acc);
     }
   }
+#else
+  // two data points per trip (lower register pressure); the generator still yields four
+  // deviates per counter block, the second pair is carried to the next trip
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int i = 0; i < n_pad; i += 2) {
+    const bool second = (i & 2) != 0;
+    if (!INJECT && !second) normals4(seed, id, (uint32_t)(i >> 2), z);
+    const float zp[2] = {second ? z[2] : z[0], second ? z[3] : z[1]};
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const RowData rd = rows[i + m];
+      double zz;
+      if (INJECT)
+        zz = (i + m < n) ? zrow[i + m] : 0.0;
+      else
+        zz = (double)zp[m];
+      const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
+      row_accumulate<M, WITH_B>(pa, pb, rd.x, yfit, rd.rerr, acc);
+    }
+  }
+#endif
 }
 
+template <bool SMEM>
+FMC_INLINE __device__ const RowData* stage_rows(const KernelArgs& a, unsigned char* smem_raw) {
+  if (!SMEM) return a.rows;
+  RowData* srows = reinterpret_cast<RowData*>(smem_raw);
+  const double2* src = reinterpret_cast<const double2*>(a.rows);
+  double2* dst = reinterpret_cast<double2*>(srows);
+  for (int i = threadIdx.x; i < 2 * a.n_pad; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return srows;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage A: the first pass of an nl2sno call (residual + Jacobian at the starting point,
+// toms573.f90:695-733 with D = 1).  Every fit does exactly the same amount of work here and
+// none needs the J(x0)^T r(x) part, so this stage runs as its own, perfectly uniform kernel:
+// one fit per thread, static assignment, no solver code.
 template <class M, bool INJECT, bool SMEM>
-__global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) bootstrap_fit_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs a) {
+  constexpr int P = M::NPARAM;
+  constexpr int PP = P * (P + 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const RowData* rows = stage_rows<SMEM>(a, smem_raw);
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= a.nres) return;
+  double x[P], h[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    x[i] = a.call == 0 ? a.start[i] : a.xbuf[i * a.cap + slot];
+    h[i] = k::dltfdj * fmax(fabs(x[i]), 1.0);  // toms573.f90:716 with D = 1
+  }
+  PassPoint<P> pa;
+  pa.set(x, h);
+  PassAcc<P> acc;
+  acc.zero();
+  const unsigned long long id = (unsigned long long)(a.first + slot);
+  const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
+  pass_loop<M, INJECT, false>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pa, acc);
+  double f, g[P], G[PP], lky[P];
+  pass_scale<P>(acc, h, h, f, g, G, lky);
+  a.init[slot] = f;
+#pragma unroll
+  for (int i = 0; i < P; ++i) a.init[(1 + i) * a.cap + slot] = g[i];
+#pragma unroll
+  for (int i = 0; i < PP; ++i) a.init[(1 + P + i) * a.cap + slot] = G[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage B: the NL2SOL iterations of one nl2sno call, one fit per thread with refill: a thread
+// that finishes takes the next fit from a shared counter, so lanes of a warp are at different
+// iterations of different fits but always execute the same thing next -- one trial pass
+// (residual + speculative Jacobian at x, Jacobian at x0 for the secant update).
+template <class M, bool INJECT, bool SMEM>
+__global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int Q = M::NPROP;
+  constexpr int PP = P * (P + 1) / 2;
   constexpr int NM = 2 * (P + Q);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[FMC_THREADS / 32];
   __shared__ unsigned int sh_rc[16];
-
-  const RowData* rows;
-  if (SMEM) {
-    RowData* srows = reinterpret_cast<RowData*>(smem_raw);
-    const double2* src = reinterpret_cast<const double2*>(a.rows);
-    double2* dst = reinterpret_cast<double2*>(srows);
-    for (int i = threadIdx.x; i < 2 * a.n_pad; i += blockDim.x) dst[i] = src[i];
-    rows = srows;
-  } else {
-    rows = a.rows;
-  }
   if (threadIdx.x < 16) sh_rc[threadIdx.x] = 0u;
+  const RowData* rows = stage_rows<SMEM>(a, smem_raw);
   __syncthreads();
 
   Nl2<P> s;
@@ -123,86 +205,116 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) bootstrap_fit_ker
   double cq[Q > 0 ? Q : 1];
   M::derived_properties(a.start, cq);
   unsigned int n_fit = 0, n_fcall = 0, n_gcall = 0, n_iter = 0, n_pass = 0;
-  int cnt[10];
-  int pass_no = 0, fit_passes = 0;
-  unsigned long long slot = 0;
+  int fit_passes = 0;
+  long long slot = 0;
   bool active = false;
 
+  // end of an nl2sno call: hand the state to the next stage, or (second call) to the sums
+  auto finish_call = [&]() {
+    if (a.call == 0) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) a.xbuf[i * a.cap + slot] = s.x[i];
+      a.istate[slot] = s.mlstgd;
+      a.istate[a.cap + slot] = s.lsvmin_ix;
+      a.cnt[0 * a.cap + slot] = s.rc;
+      a.cnt[1 * a.cap + slot] = s.nfcall;
+      a.cnt[2 * a.cap + slot] = s.ngcall;
+      a.cnt[3 * a.cap + slot] = s.niter;
+      a.cnt[4 * a.cap + slot] = fit_passes;
+      return;
+    }
+    double props[Q > 0 ? Q : 1];
+    M::derived_properties(s.x, props);  // bootstrap.f90:316
+#pragma unroll
+    for (int i = 0; i < P; ++i) {       // bootstrap.f90:317-318, on shifted values
+      const double dv = s.x[i] - a.start[i];
+      kahan_add(msum[i], mcmp[i], dv);
+      kahan_add(msum[P + i], mcmp[P + i], dv * dv);
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const double dv = props[i] - cq[i];
+      kahan_add(msum[2 * P + i], mcmp[2 * P + i], dv);
+      kahan_add(msum[2 * P + Q + i], mcmp[2 * P + Q + i], dv * dv);
+    }
+    int c0[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) c0[i] = a.cnt[i * a.cap + slot];
+    ++n_fit;
+    n_fcall += s.nfcall + c0[1];
+    n_gcall += s.ngcall + c0[2];
+    n_iter += s.niter + c0[3];
+    n_pass += fit_passes + c0[4];
+    atomicAdd(&sh_rc[s.rc & 15], 1u);
+    if (a.params_out)
+      for (int i = 0; i < P; ++i) a.params_out[slot * P + i] = s.x[i];
+    if (a.props_out)
+      for (int i = 0; i < Q; ++i) a.props_out[slot * Q + i] = props[i];
+    if (a.counters_out) {
+      int* co = a.counters_out + slot * 10;
+      for (int i = 0; i < 5; ++i) co[i] = c0[i];
+      co[5] = s.rc;
+      co[6] = s.nfcall;
+      co[7] = s.ngcall;
+      co[8] = s.niter;
+      co[9] = fit_passes;
+    }
+  };
+
+  // take the next fit: load its starting point and the sums of its initial pass (stage A),
+  // and run the solver up to its first trial point
   auto fetch = [&]() {
-    const unsigned long long kk = atomicAdd(a.next_id, 1ULL);
-    if (kk < (unsigned long long)a.nres) {
-      slot = kk;
-      s.reset_fit();
-      s.begin(a.start);
-      pass_no = 0;
-      fit_passes = 0;
+    for (;;) {
+      const unsigned long long kk = atomicAdd(a.next_id, 1ULL);
+      if (kk >= (unsigned long long)a.nres) {
+        active = false;
+        return;
+      }
+      slot = (long long)kk;
+      double xs[P];
+      if (a.call == 0) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) xs[i] = a.start[i];
+        s.reset_fit();
+      } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) xs[i] = a.xbuf[i * a.cap + slot];
+        s.mlstgd = a.istate[slot];
+        s.lsvmin_ix = a.istate[a.cap + slot];
+      }
+      s.begin(xs);
+      s.res_f = a.init[slot];
+#pragma unroll
+      for (int i = 0; i < P; ++i) s.res_g[i] = a.init[(1 + i) * a.cap + slot];
+#pragma unroll
+      for (int i = 0; i < PP; ++i) s.res_G[i] = a.init[(1 + P + i) * a.cap + slot];
+      fit_passes = 1;
       active = true;
-    } else {
-      active = false;
+      if (s.resume()) return;
+      finish_call();  // ended without a single trial step (e.g. residual too big at the start)
     }
   };
   fetch();
 
   while (__any_sync(0xffffffffu, active)) {
-    const bool anyb = __any_sync(0xffffffffu, active && s.need_b);
     if (active) {
       PassPoint<P> pa, pb;
       pa.set(s.x, s.hA);
       pb.set(s.x0, s.hJ);
       PassAcc<P> acc;
       acc.zero();
-      const unsigned long long id = (unsigned long long)a.first + slot;
-      const double* zrow = INJECT ? a.z_inject + slot * (unsigned long long)a.n : nullptr;
-      if (anyb)
-        pass_loop<M, INJECT, true>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
-      else
-        pass_loop<M, INJECT, false>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
+      const unsigned long long id = (unsigned long long)(a.first + slot);
+      const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
+      pass_loop<M, INJECT, true>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
       pass_finish<P>(acc, s);
       ++fit_passes;
-      ++n_pass;
-
       if (!s.resume()) {
-        n_fcall += s.nfcall;
-        n_gcall += s.ngcall;
-        n_iter += s.niter;
-        cnt[5 * pass_no + 0] = s.rc;
-        cnt[5 * pass_no + 1] = s.nfcall;
-        cnt[5 * pass_no + 2] = s.ngcall;
-        cnt[5 * pass_no + 3] = s.niter;
-        cnt[5 * pass_no + 4] = fit_passes;
-        fit_passes = 0;
-        if (pass_no == 0) {
-          // fit_data calls nl2sno a second time from the first answer (bootstrap.f90:223-225)
-          pass_no = 1;
-          s.begin(s.x);
-        } else {
-          double props[Q > 0 ? Q : 1];
-          M::derived_properties(s.x, props);  // bootstrap.f90:316
-#pragma unroll
-          for (int i = 0; i < P; ++i) {       // bootstrap.f90:317-318, on shifted values
-            const double dv = s.x[i] - a.start[i];
-            kahan_add(msum[i], mcmp[i], dv);
-            kahan_add(msum[P + i], mcmp[P + i], dv * dv);
-          }
-#pragma unroll
-          for (int i = 0; i < Q; ++i) {
-            const double dv = props[i] - cq[i];
-            kahan_add(msum[2 * P + i], mcmp[2 * P + i], dv);
-            kahan_add(msum[2 * P + Q + i], mcmp[2 * P + Q + i], dv * dv);
-          }
-          ++n_fit;
-          atomicAdd(&sh_rc[s.rc & 15], 1u);
-          if (a.params_out)
-            for (int i = 0; i < P; ++i) a.params_out[slot * P + i] = s.x[i];
-          if (a.props_out)
-            for (int i = 0; i < Q; ++i) a.props_out[slot * Q + i] = props[i];
-          if (a.counters_out)
-            for (int i = 0; i < 10; ++i) a.counters_out[slot * 10 + i] = cnt[i];
-          fetch();
-        }
+        finish_call();
+        fetch();
       }
     }
   }
+  if (a.call == 0) return;
 
   // ---- epilogue: warp shuffle + block reduction of the moment sums, one atomic per block
   auto block_sum = [&](double v) -> double {

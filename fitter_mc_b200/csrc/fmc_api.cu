@@ -11,7 +11,19 @@
 #include "../../include/fmc_b200.h"
 #include "model_registry.cuh"
 
-using namespace fmc;
+// (no `using namespace fmc` here: fmc::exp & co. must not leak into the global scope, where
+// they would collide with the CUDA math headers)
+using fmc::acc_len;
+using fmc::ACC_NFCALL;
+using fmc::ACC_NFIT;
+using fmc::ACC_NGCALL;
+using fmc::ACC_NITER;
+using fmc::ACC_NPASS;
+using fmc::ACC_RC;
+using fmc::KernelArgs;
+using fmc::ModelEntry;
+using fmc::normals4;
+using fmc::RowData;
 
 namespace {
 
@@ -27,8 +39,8 @@ thread_local std::string g_last_cuda_error;
   } while (0)
 
 const std::vector<ModelEntry>& models() {
-  static const std::vector<ModelEntry> m = {fmc_entry_model0(), fmc_entry_model1(), fmc_entry_model2(),
-                                            fmc_entry_model3()};
+  static const std::vector<ModelEntry> m = {fmc::fmc_entry_model0(), fmc::fmc_entry_model1(),
+                                            fmc::fmc_entry_model2(), fmc::fmc_entry_model3()};
   return m;
 }
 
@@ -92,11 +104,19 @@ struct fmc_context {
   double* acc_own = nullptr;
   double* acc = nullptr;
   int acc_n = 0;
-  unsigned long long* next_id_dev = nullptr;
   double* params_out_dev = nullptr;
   double* props_out_dev = nullptr;
-  int* counters_dev = nullptr;
+  int* counters_dev_out = nullptr;
   long long out_cap_p = 0, out_cap_q = 0, out_cap_c = 0;  // capacities in elements
+  // pipeline state between the kernels of a chunk (bootstrap_kernel.cuh)
+  double* xbuf = nullptr;
+  double* initbuf = nullptr;
+  int* istate = nullptr;
+  int* cnt = nullptr;
+  long long chunk_cap = 0;
+  int chunk_p = 0;
+  unsigned long long* counters_dev = nullptr;  // one work counter per iterate launch
+  int ncounters = 0;
   long long inflight = -1;
   bool keep = false;
   double start[16] = {0};
@@ -188,7 +208,6 @@ int fmc_create(fmc_context** out, int device) {
   c->stream = c->own_stream;
   FMC_CUDA(cudaEventCreate(&c->ev0));
   FMC_CUDA(cudaEventCreate(&c->ev1));
-  FMC_CUDA(cudaMalloc(&c->next_id_dev, sizeof(unsigned long long)));
   c->acc_n = acc_len(FMC_MAX_PARAM, FMC_MAX_PARAM);
   FMC_CUDA(cudaMalloc(&c->acc_own, sizeof(double) * c->acc_n));
   c->acc = c->acc_own;
@@ -202,10 +221,14 @@ int fmc_destroy(fmc_context* c) {
   if (c->inflight >= 0) cudaStreamSynchronize(c->stream);
   cudaFree(c->rows_dev);
   cudaFree(c->acc_own);
-  cudaFree(c->next_id_dev);
+  cudaFree(c->xbuf);
+  cudaFree(c->initbuf);
+  cudaFree(c->istate);
+  cudaFree(c->cnt);
+  cudaFree(c->counters_dev);
   cudaFree(c->params_out_dev);
   cudaFree(c->props_out_dev);
-  cudaFree(c->counters_dev);
+  cudaFree(c->counters_dev_out);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -298,13 +321,41 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
       c->out_cap_q = need_q;
     }
     if (need_c > c->out_cap_c) {
-      cudaFree(c->counters_dev);
-      c->counters_dev = nullptr;
+      cudaFree(c->counters_dev_out);
+      c->counters_dev_out = nullptr;
       c->out_cap_c = 0;
-      FMC_CUDA(cudaMalloc(&c->counters_dev, sizeof(int) * need_c));
+      FMC_CUDA(cudaMalloc(&c->counters_dev_out, sizeof(int) * need_c));
       c->out_cap_c = need_c;
     }
   }
+  // chunking: the pipeline keeps ~0.4 KB of state per fit between its kernels
+  const long long kChunk = 1LL << 21;
+  const long long cap = nresample < kChunk ? (nresample > 0 ? nresample : 1) : kChunk;
+  const int PP = P * (P + 1) / 2;
+  if (cap > c->chunk_cap || P != c->chunk_p) {
+    cudaFree(c->xbuf);
+    cudaFree(c->initbuf);
+    cudaFree(c->istate);
+    cudaFree(c->cnt);
+    c->xbuf = c->initbuf = nullptr;
+    c->istate = c->cnt = nullptr;
+    c->chunk_cap = 0;
+    FMC_CUDA(cudaMalloc(&c->xbuf, sizeof(double) * P * cap));
+    FMC_CUDA(cudaMalloc(&c->initbuf, sizeof(double) * (1 + P + PP) * cap));
+    FMC_CUDA(cudaMalloc(&c->istate, sizeof(int) * 2 * cap));
+    FMC_CUDA(cudaMalloc(&c->cnt, sizeof(int) * 10 * cap));
+    c->chunk_cap = cap;
+    c->chunk_p = P;
+  }
+  const long long nchunks = (nresample + cap - 1) / cap;
+  if (2 * nchunks > c->ncounters) {
+    cudaFree(c->counters_dev);
+    c->counters_dev = nullptr;
+    c->ncounters = 0;
+    FMC_CUDA(cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * 2 * nchunks));
+    c->ncounters = (int)(2 * nchunks);
+  }
+
   KernelArgs a;
   std::memset(&a, 0, sizeof(a));
   a.rows = c->rows_dev;
@@ -315,13 +366,11 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     c->start[i] = params_start[i];
   }
   a.seed = seed;
-  a.first = first_counter;
-  a.nres = nresample;
-  a.z_inject = z_inject_dev;
-  a.params_out = c->keep ? c->params_out_dev : nullptr;
-  a.props_out = c->keep ? c->props_out_dev : nullptr;
-  a.counters_out = c->keep ? c->counters_dev : nullptr;
-  a.next_id = c->next_id_dev;
+  a.cap = c->chunk_cap;
+  a.xbuf = c->xbuf;
+  a.init = c->initbuf;
+  a.istate = c->istate;
+  a.cnt = c->cnt;
   a.acc = c->acc;
 
   // data in shared memory when it fits (227 KB opt-in on B200), else through L1/L2
@@ -335,20 +384,35 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     g_last_cuda_error = "kernel does not fit on an SM";
     return FMC_ERR_CUDA;
   }
-  // persistent grid: every SM full, threads take resamples from a shared counter
-  long long grid = (long long)c->num_sms * bps;
-  const long long need = (nresample + FMC_THREADS - 1) / FMC_THREADS;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
-  c->geom[0] = (int)grid;
+  // persistent grid for the refill kernels: every SM full, threads take fits from a counter
+  const long long full_grid = (long long)c->num_sms * bps;
   c->geom[1] = FMC_THREADS;
   c->geom[2] = bps;
   c->geom[3] = c->num_sms;
 
-  FMC_CUDA(cudaMemsetAsync(c->next_id_dev, 0, sizeof(unsigned long long), c->stream));
+  if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 2 * nchunks, c->stream));
   FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
   FMC_CUDA(cudaEventRecord(c->ev0, c->stream));
-  if (nresample > 0) FMC_CUDA(m.launch(a, inject, smem, (int)grid, shmem, c->stream));
+  for (long long ch = 0; ch < nchunks; ++ch) {
+    const long long lo = ch * cap, cnt = (nresample - lo) < cap ? (nresample - lo) : cap;
+    a.first = first_counter + lo;
+    a.nres = cnt;
+    a.z_inject = inject ? z_inject_dev + (size_t)lo * c->n : nullptr;
+    a.params_out = c->keep ? c->params_out_dev + (size_t)lo * P : nullptr;
+    a.props_out = c->keep ? c->props_out_dev + (size_t)lo * (Q > 0 ? Q : 1) : nullptr;
+    a.counters_out = c->keep ? c->counters_dev_out + (size_t)lo * 10 : nullptr;
+    long long grid = full_grid;
+    const long long need = (cnt + FMC_THREADS - 1) / FMC_THREADS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    c->geom[0] = (int)grid;
+    for (int call = 0; call < 2; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
+      a.call = call;
+      a.next_id = c->counters_dev + 2 * ch + call;
+      FMC_CUDA(m.launch_init(a, inject, smem, shmem, c->stream));
+      FMC_CUDA(m.launch_iter(a, inject, smem, (int)grid, shmem, c->stream));
+    }
+  }
   FMC_CUDA(cudaEventRecord(c->ev1, c->stream));
   c->inflight = nresample;
   return FMC_OK;
@@ -406,7 +470,7 @@ int fmc_finish(fmc_context* c, double* sum_p, double* sum_p2, double* sum_prop, 
       FMC_CUDA(cudaMemcpyAsync(props_out, c->props_out_dev, sizeof(double) * Q * nres, cudaMemcpyDeviceToHost,
                                c->stream));
     if (counters_out)
-      FMC_CUDA(cudaMemcpyAsync(counters_out, c->counters_dev, sizeof(int) * 10 * nres, cudaMemcpyDeviceToHost,
+      FMC_CUDA(cudaMemcpyAsync(counters_out, c->counters_dev_out, sizeof(int) * 10 * nres, cudaMemcpyDeviceToHost,
                                c->stream));
   }
   FMC_CUDA(cudaStreamSynchronize(c->stream));

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "bootstrap_kernel.cuh"
 
 namespace fmc {
@@ -14,7 +16,9 @@ struct ModelEntry {
   double init[16];
   double (*model_y)(const double*, double);   // host copies of the plug-in routines
   void (*props)(const double*, double*);
-  cudaError_t (*launch)(const KernelArgs&, bool inject, bool smem, int grid, size_t shmem, cudaStream_t);
+  // stage A (uniform first pass) and stage B (refill iterations) of one nl2sno call
+  cudaError_t (*launch_init)(const KernelArgs&, bool inject, bool smem, size_t shmem, cudaStream_t);
+  cudaError_t (*launch_iter)(const KernelArgs&, bool inject, bool smem, int grid, size_t shmem, cudaStream_t);
   cudaError_t (*occupancy)(bool inject, bool smem, size_t shmem, int* blocks_per_sm);
 };
 
@@ -25,45 +29,40 @@ struct ModelBinding {
 
   template <bool INJECT, bool SMEM>
   static cudaError_t prep(size_t shmem) {
-    return cudaFuncSetAttribute(bootstrap_fit_kernel<M, INJECT, SMEM>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+    cudaError_t e = cudaFuncSetAttribute(iterate_kernel<M, INJECT, SMEM>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(init_pass_kernel<M, INJECT, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)shmem);
   }
-  static cudaError_t launch(const KernelArgs& a, bool inject, bool smem, int grid, size_t shmem,
-                            cudaStream_t st) {
-    cudaError_t e;
-#define FMC_LAUNCH(I, S)                                                         \
-  do {                                                                           \
-    e = prep<I, S>(shmem);                                                       \
-    if (e != cudaSuccess) return e;                                              \
-    bootstrap_fit_kernel<M, I, S><<<grid, FMC_THREADS, shmem, st>>>(a);          \
-    return cudaGetLastError();                                                   \
-  } while (0)
-    if (inject) {
-      if (smem) FMC_LAUNCH(true, true);
-      else FMC_LAUNCH(true, false);
-    } else {
-      if (smem) FMC_LAUNCH(false, true);
-      else FMC_LAUNCH(false, false);
-    }
-#undef FMC_LAUNCH
+  // run f(INJECT, SMEM) with the two runtime flags turned into compile-time constants
+  template <class F>
+  static cudaError_t dispatch(bool inject, bool smem, F&& f) {
+    if (inject) return smem ? f(std::true_type{}, std::true_type{}) : f(std::true_type{}, std::false_type{});
+    return smem ? f(std::false_type{}, std::true_type{}) : f(std::false_type{}, std::false_type{});
+  }
+
+  static cudaError_t launch_init(const KernelArgs& a, bool inject, bool smem, size_t shmem, cudaStream_t st) {
+    const int grid = (int)((a.nres + FMC_THREADS - 1) / FMC_THREADS);
+    return dispatch(inject, smem, [&](auto I, auto S) {
+      init_pass_kernel<M, decltype(I)::value, decltype(S)::value><<<grid, FMC_THREADS, shmem, st>>>(a);
+      return cudaGetLastError();
+    });
+  }
+  static cudaError_t launch_iter(const KernelArgs& a, bool inject, bool smem, int grid, size_t shmem,
+                                 cudaStream_t st) {
+    return dispatch(inject, smem, [&](auto I, auto S) {
+      iterate_kernel<M, decltype(I)::value, decltype(S)::value><<<grid, FMC_THREADS, shmem, st>>>(a);
+      return cudaGetLastError();
+    });
   }
   static cudaError_t occupancy(bool inject, bool smem, size_t shmem, int* nb) {
-    cudaError_t e;
-#define FMC_OCC(I, S)                                                                           \
-  do {                                                                                          \
-    e = prep<I, S>(shmem);                                                                      \
-    if (e != cudaSuccess) return e;                                                             \
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, bootstrap_fit_kernel<M, I, S>,     \
-                                                         FMC_THREADS, shmem);                   \
-  } while (0)
-    if (inject) {
-      if (smem) FMC_OCC(true, true);
-      else FMC_OCC(true, false);
-    } else {
-      if (smem) FMC_OCC(false, true);
-      else FMC_OCC(false, false);
-    }
-#undef FMC_OCC
+    return dispatch(inject, smem, [&](auto I, auto S) {
+      cudaError_t e = prep<decltype(I)::value, decltype(S)::value>(shmem);
+      if (e != cudaSuccess) return e;
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          nb, iterate_kernel<M, decltype(I)::value, decltype(S)::value>, FMC_THREADS, shmem);
+    });
   }
   static ModelEntry entry() {
     ModelEntry e{};
@@ -80,7 +79,8 @@ struct ModelBinding {
     }
     e.model_y = host_model_y;
     e.props = host_props;
-    e.launch = launch;
+    e.launch_init = launch_init;
+    e.launch_iter = launch_iter;
     e.occupancy = occupancy;
     return e;
   }

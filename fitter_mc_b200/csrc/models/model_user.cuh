@@ -14,6 +14,7 @@
 #pragma once
 #include "../fmc_common.cuh"
 #include "../fast_math.cuh"
+#include "../pert.cuh"
 
 namespace fmc {
 
@@ -37,7 +38,11 @@ struct ModelUser {
 
   // The model function.
   // YOU NEED TO CHANGE THIS ROUTINE IF YOU HAVE A NEW MODEL.
-  FMC_HD static FMC_INLINE double model_y(const double* params, double x) {
+  // Keep it generic in the scalar type T (write the formula once, as you would for double):
+  // the engine then gets nl2sno's forward differences from one evaluation (pert.cuh).  A
+  // plain `static double model_y(const double* params, double x)` also works, just slower.
+  template <class T>
+  FMC_HD static FMC_INLINE T model_y(const T* params, double x) {
     return params[0] + params[1] * exp(-params[2] * x);
   }
 

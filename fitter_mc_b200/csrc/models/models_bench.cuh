@@ -4,6 +4,7 @@
 #pragma once
 #include "../fmc_common.cuh"
 #include "../fast_math.cuh"
+#include "../pert.cuh"
 
 namespace fmc {
 
@@ -24,7 +25,8 @@ struct ModelTest4 {
     params_init[2] = 1.0;
     params_init[3] = 0.0;
   }
-  FMC_HD static FMC_INLINE double model_y(const double* params, double x) {
+  template <class T>
+  FMC_HD static FMC_INLINE T model_y(const T* params, double x) {
     return params[0] + params[1] * exp(-params[2] * x) + params[3] * x;
   }
   FMC_HD static FMC_INLINE void derived_properties(const double* params, double* props) {
@@ -48,11 +50,12 @@ struct ModelPeaks10 {
     }
     for (int i = 0; i < 3; ++i) (*prop_name)[i] = qn[i];
   }
-  FMC_HD static FMC_INLINE double model_y(const double* params, double x) {
-    double y = params[0];
+  template <class T>
+  FMC_HD static FMC_INLINE T model_y(const T* params, double x) {
+    T y = params[0];
 #pragma unroll
     for (int kk = 0; kk < 3; ++kk) {
-      double u = (x - params[2 + 3 * kk]) / params[3 + 3 * kk];
+      const T u = (x - params[2 + 3 * kk]) / params[3 + 3 * kk];
       y = y + params[1 + 3 * kk] * exp(-0.5 * (u * u));
     }
     return y;
@@ -78,7 +81,8 @@ struct ModelStiff4 {
     (*prop_name)[1] = "ac";
     for (int i = 0; i < 4; ++i) params_init[i] = 1.0;
   }
-  FMC_HD static FMC_INLINE double model_y(const double* params, double x) {
+  template <class T>
+  FMC_HD static FMC_INLINE T model_y(const T* params, double x) {
     return params[0] * exp(-params[1] * x) + params[2] * pow(x, -params[3]);
   }
   FMC_HD static FMC_INLINE void derived_properties(const double* params, double* props) {

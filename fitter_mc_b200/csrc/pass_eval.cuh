@@ -8,21 +8,49 @@
 //   dupdat/qrfact    column norms and J^T J                               toms573.f90:2458, 4360-4567
 //   nl2itr label 380 lky = J(x0)^T r(x)                                   toms573.f90:1268-1293
 // Nothing of length n is written: the row is consumed as soon as it is formed.
+//
+// Arithmetic form (all in FP64).  With m0 = model_y(x; x_i), mk = model_y(x + h_k e_k; x_i) and
+// w = 1/err_i:
+//     r_i(x + h_k e_k) - r_i(x) = (y' - mk) w - (y' - m0) w = (m0 - mk) w
+// so the Jacobian row is formed from the model differences dm_k = m0 - mk, which do not
+// involve the resampled y' at all.  The reference subtracts the two rounded residuals
+// instead; both carry the same ~1e-8 relative forward-difference noise, from rounding in the
+// model values themselves, so neither is the more accurate.  The 1/h_k column factors are
+// constants of a pass and are applied once to the p x p sums (pass_finish), not n times.
+// Per row this needs  (p+1) model values, p subtractions, and for the sums
+//     t = w r,  f += r r,  g_k += dm_k t,  G_kl += (dm_k w^2) dm_l,  lky_k += dmB_k t.
 #pragma once
+#include <type_traits>
+#include <utility>
+
 #include "fmc_common.cuh"
+#include "pert.cuh"
 
 namespace fmc {
+
+// Does the plug-in provide a model_y that is generic in its scalar type (see pert.cuh)?
+template <class M, class = void>
+struct has_generic_model : std::false_type {};
+template <class M>
+struct has_generic_model<M, std::void_t<decltype(M::model_y(std::declval<const Pert*>(), 0.0))>> : std::true_type {};
+#ifdef FMC_FD_PLAIN
+template <class M>
+constexpr bool use_pert_v = false;  // force the p+1 plain evaluations (validation builds)
+#else
+template <class M>
+constexpr bool use_pert_v = has_generic_model<M>::value;
+#endif
 
 // An evaluation point with its finite-difference steps, held in registers for a whole pass.
 template <int P>
 struct PassPoint {
-  double x[P];   // parameters
-  double xh[P];  // x[k] + h[k]: the k-th perturbed coordinate (toms573.f90:718)
-  FMC_HD FMC_INLINE void set(const double* xs, const double* h) {
+  double x[P];  // parameters
+  double h[P];  // forward-difference steps (toms573.f90:716)
+  FMC_HD FMC_INLINE void set(const double* xs, const double* hs) {
 #pragma unroll
     for (int kk = 0; kk < P; ++kk) {
       x[kk] = xs[kk];
-      xh[kk] = xs[kk] + h[kk];
+      h[kk] = hs[kk];
     }
   }
 };
@@ -46,25 +74,34 @@ struct PassAcc {
   }
 };
 
-// Residual and UNSCALED Jacobian row at `pt` for the data point (xi, yfit, 1/err):
-// D[k] = r(x + h_k e_k) - r(x).  The division by h_k of toms573.f90:729-732 is a constant
-// factor per column, so it is applied once per pass to the p x p sums (pass_finish) instead
-// of n times per column -- same value up to one rounding per term, 2p fewer FP64 ops per row.
-// Because the
-// model is inlined p+1 times with all but one coordinate identical, common subexpressions
-// (e.g. exp(-al*x) of the default model for every column except al's) are evaluated once.
+// Model value m0 = model_y(x; xi) and model differences dm[k] = m0 - model_y(x + h_k e_k; xi).
+//  * generic plug-in (template <class T> model_y): ONE evaluation of the model's expensive
+//    parts; the p differences come from perturbation arithmetic (pert.cuh).
+//  * double-only plug-in: p+1 plain evaluations, as nl2sno does (toms573.f90:714-733).  The
+//    model is inlined p+1 times with all but one coordinate identical, so the compiler still
+//    shares common subexpressions (e.g. exp(-al*x) for every column except al's).
 template <class M>
-FMC_HD FMC_INLINE void row_eval(const PassPoint<M::NPARAM>& pt, double xi, double yfit, double rerr,
-                                double& r0, double (&D)[M::NPARAM]) {
+FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, double& m0,
+                                 double (&dm)[M::NPARAM]) {
   constexpr int P = M::NPARAM;
-  r0 = (yfit - M::model_y(pt.x, xi)) * rerr;
+  m0 = M::model_y(pt.x, xi);
+  if constexpr (use_pert_v<M>) {
 #pragma unroll
-  for (int kk = 0; kk < P; ++kk) {
-    double xs[P];
+    for (int kk = 0; kk < P; ++kk) {
+      Pert xs[P];
 #pragma unroll
-    for (int m = 0; m < P; ++m) xs[m] = (m == kk) ? pt.xh[m] : pt.x[m];
-    const double rk = (yfit - M::model_y(xs, xi)) * rerr;
-    D[kk] = rk - r0;
+      for (int m = 0; m < P; ++m) xs[m] = Pert(pt.x[m], (m == kk) ? pt.h[m] : 0.0, m == kk);
+      const Pert mk = M::model_y(xs, xi);
+      dm[kk] = -mk.d;
+    }
+  } else {
+#pragma unroll
+    for (int kk = 0; kk < P; ++kk) {
+      double xs[P];
+#pragma unroll
+      for (int m = 0; m < P; ++m) xs[m] = (m == kk) ? pt.x[m] + pt.h[m] : pt.x[m];
+      dm[kk] = m0 - M::model_y(xs, xi);
+    }
   }
 }
 
@@ -73,48 +110,58 @@ template <class M, bool WITH_B>
 FMC_HD FMC_INLINE void row_accumulate(const PassPoint<M::NPARAM>& a, const PassPoint<M::NPARAM>& b,
                                       double xi, double yfit, double rerr, PassAcc<M::NPARAM>& acc) {
   constexpr int P = M::NPARAM;
-  double ra, Ja[P];
-  row_eval<M>(a, xi, yfit, rerr, ra, Ja);
-  acc.f = fma(ra, ra, acc.f);
+  double m0, dma[P];
+  row_model<M>(a, xi, m0, dma);
+  const double r = (yfit - m0) * rerr;  // madr, bootstrap.f90:247
+  const double t = rerr * r;
+  const double w2 = rerr * rerr;
+  acc.f = fma(r, r, acc.f);
   int m = 0;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    acc.g[i] = fma(Ja[i], ra, acc.g[i]);
+    acc.g[i] = fma(dma[i], t, acc.g[i]);
+    const double dw = dma[i] * w2;
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
-      acc.G[m] = fma(Ja[i], Ja[j], acc.G[m]);
+      acc.G[m] = fma(dw, dma[j], acc.G[m]);
       ++m;
     }
   }
   if (WITH_B) {
-    double rb, Jb[P];
-    row_eval<M>(b, xi, yfit, rerr, rb, Jb);
+    double mb, dmb[P];
+    row_model<M>(b, xi, mb, dmb);
 #pragma unroll
-    for (int i = 0; i < P; ++i) acc.lky[i] = fma(Jb[i], ra, acc.lky[i]);
+    for (int i = 0; i < P; ++i) acc.lky[i] = fma(dmb[i], t, acc.lky[i]);
   }
 }
 
-// Apply the 1/h_k column factors to the sums of a finished pass and hand them to the solver.
-template <int P, class Solver>
-FMC_HD FMC_INLINE void pass_finish(const PassAcc<P>& acc, Solver& s) {
+// Apply the 1/h_k column factors to the sums of a finished pass: res = (f, g[P], G[PP], lky[P]).
+template <int P>
+FMC_HD FMC_INLINE void pass_scale(const PassAcc<P>& acc, const double* hA, const double* hB, double& res_f,
+                                  double* res_g, double* res_G, double* res_lky) {
   double ia[P], ib[P];
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    ia[i] = 1.0 / s.hA[i];
-    ib[i] = 1.0 / s.hJ[i];
+    ia[i] = 1.0 / hA[i];
+    ib[i] = 1.0 / hB[i];
   }
-  s.res_f = acc.f;
+  res_f = acc.f;
   int m = 0;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    s.res_g[i] = acc.g[i] * ia[i];
-    s.res_lky[i] = acc.lky[i] * ib[i];
+    res_g[i] = acc.g[i] * ia[i];
+    res_lky[i] = acc.lky[i] * ib[i];
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
-      s.res_G[m] = acc.G[m] * (ia[i] * ia[j]);
+      res_G[m] = acc.G[m] * (ia[i] * ia[j]);
       ++m;
     }
   }
+}
+
+template <int P, class Solver>
+FMC_HD FMC_INLINE void pass_finish(const PassAcc<P>& acc, Solver& s) {
+  pass_scale<P>(acc, s.hA, s.hJ, s.res_f, s.res_g, s.res_G, s.res_lky);
 }
 
 }  // namespace fmc

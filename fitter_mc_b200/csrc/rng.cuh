@@ -15,6 +15,10 @@
 
 #include "fmc_common.cuh"
 
+#ifndef FMC_PHILOX_ROUNDS
+#define FMC_PHILOX_ROUNDS 10
+#endif
+
 namespace fmc {
 
 struct U4 {
@@ -35,7 +39,7 @@ FMC_HD FMC_INLINE void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t&
 // Philox4x32-10 (Salmon et al., SC'11).  Known answers are checked in tests/test_rng.py.
 FMC_HD FMC_INLINE U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < FMC_PHILOX_ROUNDS; ++r) {
     uint32_t hi0, lo0, hi1, lo1;
     mulhilo32(0xD2511F53u, c.x, hi0, lo0);
     mulhilo32(0xCD9E8D57u, c.z, hi1, lo1);

@@ -90,6 +90,24 @@ int bootstrap(int n, const double* x, const double* y, const double* err, const 
   return 0;
 }
 
+
+// model value and forward differences dm[k] = m(x) - m(x + h_k e_k) through (a) the product's
+// row_model (perturbation arithmetic for generic plug-ins) and (b) p+1 plain evaluations
+template <class M>
+void row_model_both(const double* x, const double* h, double xi, double* m0, double* dm_engine, double* dm_plain) {
+  constexpr int P = M::NPARAM;
+  PassPoint<P> pt;
+  pt.set(x, h);
+  double dm[P];
+  row_model<M>(pt, xi, *m0, dm);
+  for (int kk = 0; kk < P; ++kk) {
+    dm_engine[kk] = dm[kk];
+    double xs[P];
+    for (int m = 0; m < P; ++m) xs[m] = (m == kk) ? x[m] + h[m] : x[m];
+    dm_plain[kk] = *m0 - M::model_y(xs, xi);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -113,6 +131,27 @@ int emul_bootstrap(int model, int n, const double* x, const double* y, const dou
     case 1: return bootstrap<ModelTest4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
     case 2: return bootstrap<ModelPeaks10>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
     case 3: return bootstrap<ModelStiff4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
+  }
+  return -1;
+}
+
+int emul_row_model(int model, const double* x, const double* h, double xi, double* m0, double* dm_engine,
+                   double* dm_plain) {
+  switch (model) {
+    case 0: row_model_both<ModelUser>(x, h, xi, m0, dm_engine, dm_plain); return 0;
+    case 1: row_model_both<ModelTest4>(x, h, xi, m0, dm_engine, dm_plain); return 0;
+    case 2: row_model_both<ModelPeaks10>(x, h, xi, m0, dm_engine, dm_plain); return 0;
+    case 3: row_model_both<ModelStiff4>(x, h, xi, m0, dm_engine, dm_plain); return 0;
+  }
+  return -1;
+}
+
+int emul_uses_pert(int model) {
+  switch (model) {
+    case 0: return use_pert_v<ModelUser>;
+    case 1: return use_pert_v<ModelTest4>;
+    case 2: return use_pert_v<ModelPeaks10>;
+    case 3: return use_pert_v<ModelStiff4>;
   }
   return -1;
 }

@@ -34,35 +34,50 @@ int run(int argc, char** argv) {
     else rows[i] = {x[n - 1], 0.0, 0.0, 0.0};
   }
   RowData* drows;
-  double* acc;
+  double *acc, *xbuf, *initb;
+  int *istate, *cnt;
   unsigned long long* next;
-  constexpr int P = VARIANT_MODEL::NPARAM, Q = VARIANT_MODEL::NPROP;
+  constexpr int P = VARIANT_MODEL::NPARAM, Q = VARIANT_MODEL::NPROP, PP = P * (P + 1) / 2;
   CK(cudaMalloc(&drows, sizeof(RowData) * n_pad));
   CK(cudaMalloc(&acc, sizeof(double) * acc_len(P, Q)));
-  CK(cudaMalloc(&next, 8));
+  CK(cudaMalloc(&next, 16));
+  CK(cudaMalloc(&xbuf, sizeof(double) * P * nres));
+  CK(cudaMalloc(&initb, sizeof(double) * (1 + P + PP) * nres));
+  CK(cudaMalloc(&istate, sizeof(int) * 2 * nres));
+  CK(cudaMalloc(&cnt, sizeof(int) * 10 * nres));
   CK(cudaMemcpy(drows, rows.data(), sizeof(RowData) * n_pad, cudaMemcpyHostToDevice));
   KernelArgs a{};
   a.rows = drows; a.n = n; a.n_pad = n_pad;
   for (int i = 0; i < P; ++i) a.start[i] = start[i];
-  a.seed = 31415; a.nres = nres; a.next_id = next; a.acc = acc;
+  a.seed = 31415; a.nres = nres; a.cap = nres; a.acc = acc;
+  a.xbuf = xbuf; a.init = initb; a.istate = istate; a.cnt = cnt;
   size_t shmem = sizeof(RowData) * n_pad;
-  auto kern = bootstrap_fit_kernel<VARIANT_MODEL, false, true>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+  auto kinit = init_pass_kernel<VARIANT_MODEL, false, true>;
+  auto kiter = iterate_kernel<VARIANT_MODEL, false, true>;
+  CK(cudaFuncSetAttribute(kinit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+  CK(cudaFuncSetAttribute(kiter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
   int bps = 0, sms = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, FMC_THREADS, shmem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kiter, FMC_THREADS, shmem));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-  cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, kern));
+  cudaFuncAttributes fa, fb;
+  CK(cudaFuncGetAttributes(&fa, kiter));
+  CK(cudaFuncGetAttributes(&fb, kinit));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 1e30f;
   std::vector<double> hacc(acc_len(P, Q));
+  const int ginit = (int)((nres + FMC_THREADS - 1) / FMC_THREADS);
   for (int r = 0; r < reps; ++r) {
     a.first = r * nres;
-    CK(cudaMemset(next, 0, 8));
+    CK(cudaMemset(next, 0, 16));
     CK(cudaMemset(acc, 0, sizeof(double) * acc_len(P, Q)));
     cudaEventRecord(e0);
-    kern<<<sms * bps, FMC_THREADS, shmem>>>(a);
+    for (int call = 0; call < 2; ++call) {
+      a.call = call;
+      a.next_id = next + call;
+      kinit<<<ginit, FMC_THREADS, shmem>>>(a);
+      kiter<<<sms * bps, FMC_THREADS, shmem>>>(a);
+    }
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -70,8 +85,8 @@ int run(int argc, char** argv) {
   }
   CK(cudaMemcpy(hacc.data(), acc, sizeof(double) * hacc.size(), cudaMemcpyDeviceToHost));
   const int NM = 2 * (P + Q);
-  printf("threads=%d minblocks=%d regs=%d local=%zu bps=%d grid=%d | nres=%lld best %.3f ms -> %.4e fits/s | nfit %.0f mean0 %.9f passes/fit %.3f\n",
-         FMC_THREADS, FMC_MIN_BLOCKS, fa.numRegs, fa.localSizeBytes, bps, sms * bps, nres, best, nres / (best * 1e-3),
+  printf("threads=%d minblocks=%d regs(iter)=%d local=%zu regs(init)=%d bps=%d grid=%d | nres=%lld best %.3f ms -> %.4e fits/s | nfit %.0f mean0 %.9f passes/fit %.3f\n",
+         FMC_THREADS, FMC_MIN_BLOCKS, fa.numRegs, fa.localSizeBytes, fb.numRegs, bps, sms * bps, nres, best, nres / (best * 1e-3),
          hacc[NM + ACC_NFIT], start[0] + hacc[0] / hacc[NM + ACC_NFIT], hacc[NM + ACC_NPASS] / hacc[NM + ACC_NFIT]);
   return 0;
 }
