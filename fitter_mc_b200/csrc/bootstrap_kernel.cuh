@@ -91,7 +91,27 @@ FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, in
                                      const double* __restrict__ zrow,
                                      const PassPoint<M::NPARAM>& pa, const PassPoint<M::NPARAM>& pb,
                                      PassAcc<M::NPARAM>& acc) {
-#if FMC_ROWS_PER_ITER == 4
+#if FMC_ROWS_PER_ITER == 4 && defined(FMC_PIPELINE_RNG)
+  // software-pipelined generator: the deviates of the NEXT four points are produced while the
+  // FP64 work of the current four is in flight (independent instruction streams in one body)
+  float zn[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!INJECT) normals4(seed, id, 0u, zn);
+  for (int i = 0; i < n_pad; i += 4) {
+    float z[4] = {zn[0], zn[1], zn[2], zn[3]};
+    if (!INJECT) normals4(seed, id, (uint32_t)((i >> 2) + 1), zn);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const RowData rd = rows[i + m];
+      double zz;
+      if (INJECT)
+        zz = (i + m < n) ? zrow[i + m] : 0.0;
+      else
+        zz = (double)z[m];
+      const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
+      row_accumulate<M, WITH_B>(pa, pb, rd.x, yfit, rd.rerr, acc);
+    }
+  }
+#elif FMC_ROWS_PER_ITER == 4
   for (int i = 0; i < n_pad; i += 4) {
     float z[4];
     if (!INJECT) normals4(seed, id, (uint32_t)(i >> 2), z);
@@ -148,7 +168,10 @@ FMC_INLINE __device__ const RowData* stage_rows(const KernelArgs& a, unsigned ch
 // none needs the J(x0)^T r(x) part, so this stage runs as its own, perfectly uniform kernel:
 // one fit per thread, static assignment, no solver code.
 template <class M, bool INJECT, bool SMEM>
-__global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs a) {
+#ifndef FMC_INIT_MIN_BLOCKS
+#define FMC_INIT_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(FMC_THREADS, FMC_INIT_MIN_BLOCKS) init_pass_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int PP = P * (P + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -175,6 +198,101 @@ __global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs
   for (int i = 0; i < P; ++i) a.init[(1 + i) * a.cap + slot] = g[i];
 #pragma unroll
   for (int i = 0; i < PP; ++i) a.init[(1 + P + i) * a.cap + slot] = G[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Stage A for the FIRST nl2sno call: every fit starts from the same point params_start with
+// the same steps h, and the model differences dm_k do not involve the resampled y' at all
+// (pass_eval.cuh), so the Jacobian rows J(x_start) -- and hence G = J^T J -- are the same for
+// every resample.  jac0_kernel evaluates them once per launch; init_shared_kernel then needs,
+// per fit and data point, only r = (y' - m0) w:  f += r^2,  g_k += (dm_k w) r  (8 FP64
+// operations instead of a model evaluation).
+//   rowJ[i][0] = m0_i,  rowJ[i][1+k] = dm_ik / err_i     (unscaled by 1/h_k)
+template <class M>
+__global__ void jac0_kernel(const KernelArgs a, double* __restrict__ rowJ, double* __restrict__ G0) {
+  constexpr int P = M::NPARAM;
+  constexpr int PP = P * (P + 1) / 2;
+  double x[P], h[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    x[i] = a.start[i];
+    h[i] = k::dltfdj * fmax(fabs(x[i]), 1.0);
+  }
+  PassPoint<P> pt;
+  pt.set(x, h);
+  for (int i = threadIdx.x; i < a.n_pad; i += blockDim.x) {
+    const RowData rd = a.rows[i];
+    double m0, dm[P];
+    row_model<M>(pt, rd.x, m0, dm);
+    rowJ[i * (1 + P)] = m0;
+#pragma unroll
+    for (int kk = 0; kk < P; ++kk) rowJ[i * (1 + P) + 1 + kk] = dm[kk] * rd.rerr;
+  }
+  __syncthreads();
+  if (threadIdx.x < PP) {  // thread m sums element m of the lower triangle, rows in order
+    int ki = 0, kj = 0, m = 0;
+    for (int i = 0; i < P; ++i)
+      for (int j = 0; j <= i; ++j) {
+        if (m == (int)threadIdx.x) {
+          ki = i;
+          kj = j;
+        }
+        ++m;
+      }
+    double sum = 0.0;
+    for (int i = 0; i < a.n_pad; ++i) sum = fma(rowJ[i * (1 + P) + 1 + ki], rowJ[i * (1 + P) + 1 + kj], sum);
+    G0[threadIdx.x] = sum * ((1.0 / h[ki]) * (1.0 / h[kj]));
+  }
+}
+
+template <class M, bool INJECT>
+__global__ void __launch_bounds__(FMC_THREADS) init_shared_kernel(const KernelArgs a,
+                                                                  const double* __restrict__ rowJ,
+                                                                  const double* __restrict__ G0) {
+  constexpr int P = M::NPARAM;
+  constexpr int PP = P * (P + 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowData* rows = reinterpret_cast<RowData*>(smem_raw);
+  double* sJ = reinterpret_cast<double*>(smem_raw + sizeof(RowData) * a.n_pad);
+  {
+    const double2* src = reinterpret_cast<const double2*>(a.rows);
+    double2* dst = reinterpret_cast<double2*>(rows);
+    for (int i = threadIdx.x; i < 2 * a.n_pad; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (1 + P) * a.n_pad; i += blockDim.x) sJ[i] = rowJ[i];
+  }
+  __syncthreads();
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= a.nres) return;
+  const unsigned long long id = (unsigned long long)(a.first + slot);
+  const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
+  double f = 0.0, g[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) g[i] = 0.0;
+  for (int i = 0; i < a.n_pad; i += 4) {
+    float z[4];
+    if (!INJECT) normals4(a.seed, id, (uint32_t)(i >> 2), z);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const RowData rd = rows[i + m];
+      double zz;
+      if (INJECT)
+        zz = (i + m < a.n) ? zrow[i + m] : 0.0;
+      else
+        zz = (double)z[m];
+      const double yfit = fma(zz, rd.err, rd.y);
+      const double* jr = sJ + (i + m) * (1 + P);
+      const double r = (yfit - jr[0]) * rd.rerr;
+      f = fma(r, r, f);
+#pragma unroll
+      for (int kk = 0; kk < P; ++kk) g[kk] = fma(jr[1 + kk], r, g[kk]);
+    }
+  }
+  a.init[slot] = f;
+#pragma unroll
+  for (int i = 0; i < P; ++i)
+    a.init[(1 + i) * a.cap + slot] = g[i] * (1.0 / (k::dltfdj * fmax(fabs(a.start[i]), 1.0)));
+#pragma unroll
+  for (int i = 0; i < PP; ++i) a.init[(1 + P + i) * a.cap + slot] = G0[i];
 }
 
 // ---------------------------------------------------------------------------------------

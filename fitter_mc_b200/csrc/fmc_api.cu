@@ -116,6 +116,8 @@ struct fmc_context {
   long long chunk_cap = 0;
   int chunk_p = 0;
   unsigned long long* counters_dev = nullptr;  // one work counter per iterate launch
+  double* rowj_dev = nullptr;  // [n_pad][1+P] shared Jacobian rows at params_start + [PP] G0
+  long long rowj_cap = 0;
   int ncounters = 0;
   long long inflight = -1;
   bool keep = false;
@@ -226,6 +228,7 @@ int fmc_destroy(fmc_context* c) {
   cudaFree(c->istate);
   cudaFree(c->cnt);
   cudaFree(c->counters_dev);
+  cudaFree(c->rowj_dev);
   cudaFree(c->params_out_dev);
   cudaFree(c->props_out_dev);
   cudaFree(c->counters_dev_out);
@@ -390,9 +393,26 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   c->geom[2] = bps;
   c->geom[3] = c->num_sms;
 
+  // first nl2sno call: shared Jacobian at params_start when its rows fit in shared memory too
+  const size_t shmem_shared = (sizeof(RowData) + sizeof(double) * (1 + P)) * (size_t)c->n_pad;
+  const bool shared_init = shmem_shared + 1024 <= (size_t)c->max_smem_optin;
+  double* g0_dev = nullptr;
+  if (shared_init) {
+    const long long need = (long long)(1 + P) * c->n_pad + PP;
+    if (need > c->rowj_cap) {
+      cudaFree(c->rowj_dev);
+      c->rowj_dev = nullptr;
+      c->rowj_cap = 0;
+      FMC_CUDA(cudaMalloc(&c->rowj_dev, sizeof(double) * need));
+      c->rowj_cap = need;
+    }
+    g0_dev = c->rowj_dev + (size_t)(1 + P) * c->n_pad;
+  }
+
   if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 2 * nchunks, c->stream));
   FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
   FMC_CUDA(cudaEventRecord(c->ev0, c->stream));
+  if (shared_init && nresample > 0) FMC_CUDA(m.launch_jac0(a, c->rowj_dev, g0_dev, c->stream));
   for (long long ch = 0; ch < nchunks; ++ch) {
     const long long lo = ch * cap, cnt = (nresample - lo) < cap ? (nresample - lo) : cap;
     a.first = first_counter + lo;
@@ -409,7 +429,10 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     for (int call = 0; call < 2; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
       a.call = call;
       a.next_id = c->counters_dev + 2 * ch + call;
-      FMC_CUDA(m.launch_init(a, inject, smem, shmem, c->stream));
+      if (call == 0 && shared_init)
+        FMC_CUDA(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
+      else
+        FMC_CUDA(m.launch_init(a, inject, smem, shmem, c->stream));
       FMC_CUDA(m.launch_iter(a, inject, smem, (int)grid, shmem, c->stream));
     }
   }

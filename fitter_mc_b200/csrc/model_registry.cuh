@@ -18,6 +18,10 @@ struct ModelEntry {
   void (*props)(const double*, double*);
   // stage A (uniform first pass) and stage B (refill iterations) of one nl2sno call
   cudaError_t (*launch_init)(const KernelArgs&, bool inject, bool smem, size_t shmem, cudaStream_t);
+  // shared-Jacobian variant of stage A for the first call (all fits start at params_start)
+  cudaError_t (*launch_jac0)(const KernelArgs&, double* rowJ, double* G0, cudaStream_t);
+  cudaError_t (*launch_init_shared)(const KernelArgs&, const double* rowJ, const double* G0, bool inject,
+                                    size_t shmem, cudaStream_t);
   cudaError_t (*launch_iter)(const KernelArgs&, bool inject, bool smem, int grid, size_t shmem, cudaStream_t);
   cudaError_t (*occupancy)(bool inject, bool smem, size_t shmem, int* blocks_per_sm);
 };
@@ -48,6 +52,25 @@ struct ModelBinding {
       init_pass_kernel<M, decltype(I)::value, decltype(S)::value><<<grid, FMC_THREADS, shmem, st>>>(a);
       return cudaGetLastError();
     });
+  }
+  static cudaError_t launch_jac0(const KernelArgs& a, double* rowJ, double* G0, cudaStream_t st) {
+    jac0_kernel<M><<<1, 1024, 0, st>>>(a, rowJ, G0);
+    return cudaGetLastError();
+  }
+  static cudaError_t launch_init_shared(const KernelArgs& a, const double* rowJ, const double* G0, bool inject,
+                                        size_t shmem, cudaStream_t st) {
+    const int grid = (int)((a.nres + FMC_THREADS - 1) / FMC_THREADS);
+    cudaError_t e;
+    if (inject) {
+      e = cudaFuncSetAttribute(init_shared_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+      if (e != cudaSuccess) return e;
+      init_shared_kernel<M, true><<<grid, FMC_THREADS, shmem, st>>>(a, rowJ, G0);
+    } else {
+      e = cudaFuncSetAttribute(init_shared_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+      if (e != cudaSuccess) return e;
+      init_shared_kernel<M, false><<<grid, FMC_THREADS, shmem, st>>>(a, rowJ, G0);
+    }
+    return cudaGetLastError();
   }
   static cudaError_t launch_iter(const KernelArgs& a, bool inject, bool smem, int grid, size_t shmem,
                                  cudaStream_t st) {
@@ -81,6 +104,8 @@ struct ModelBinding {
     e.props = host_props;
     e.launch_init = launch_init;
     e.launch_iter = launch_iter;
+    e.launch_jac0 = launch_jac0;
+    e.launch_init_shared = launch_init_shared;
     e.occupancy = occupancy;
     return e;
   }

@@ -38,9 +38,11 @@ FMC_HD FMC_INLINE double dotn(int n, const double* x, const double* y) {  // dot
   return s;
 }
 
-// v2norm (toms573.f90:4789): scaled 2-norm; kept in the scaled form for p-vectors so the
-// many threshold tests downstream see the same rounding as the reference.
-FMC_HD inline double nrm2(int n, const double* x) {
+// v2norm (toms573.f90:4789-4838).  The reference's scaled recurrence (one divide per element)
+// only exists to dodge overflow/underflow of the squares; for p-vectors in the normal range
+// sqrt(sum x^2) is the same number to within an ulp, so that is what is evaluated, and the
+// scaled recurrence is kept as the fallback when the plain sum leaves the normal range.
+FMC_HD inline double nrm2_scaled(int n, const double* x) {
   int i = 0;
   for (; i < n; ++i)
     if (x[i] != 0.0) break;
@@ -61,6 +63,12 @@ FMC_HD inline double nrm2(int n, const double* x) {
     }
   }
   return scale * sqrt(t);
+}
+FMC_HD FMC_INLINE double nrm2(int n, const double* x) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s = fma(x[i], x[i], s);
+  if (s > 1e-280 && s < 1e280) return sqrt(s);
+  return nrm2_scaled(n, x);
 }
 
 // Solve (L**T) x = y, L packed lower-by-rows (litvmu, toms573.f90:3334).

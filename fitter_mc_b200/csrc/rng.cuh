@@ -6,10 +6,10 @@
 //   bits    = Philox4x32-10( key = (seed_lo, seed_hi), counter = (point/4, 0, resample_lo, resample_hi) )
 //   z[4k..4k+3] = two Box-Muller pairs from the four 32-bit words of block k
 //
-// The deviates are evaluated in FP32: they carry the same ~24 bits of resolution as the
-// reference's (which are built from 24-bit RANLUX uniforms), and the FP32/SFU work runs in
-// issue slots the FP64 pipe leaves free, so regenerating z in every pass over the data costs
-// no FP64 throughput and no memory.
+// The deviates are evaluated in FP32 (by default with the SFU's lg2/rsq/sin/cos): they carry
+// about the resolution of the reference's, which are built from 24-bit RANLUX uniforms, and
+// the INT32/FP32/SFU work runs in issue slots the half-rate FP64 pipe leaves free, so
+// regenerating z in every pass over the data costs no FP64 throughput and no memory.
 #pragma once
 #include <cstring>
 
@@ -85,6 +85,18 @@ FMC_HD FMC_INLINE float ln_pos_normal(float u) {
 
 FMC_HD FMC_INLINE void normal_pair(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // 2^-32
+#if defined(__CUDA_ARCH__) && !defined(FMC_ACCURATE_NORMALS)
+  // SFU path (MUFU lg2/rsq/sin/cos, ~1e-6 relative): +8 % fits/s on C2 versus the polynomial
+  // path below, which -DFMC_ACCURATE_NORMALS selects.  Either way the deviates are what
+  // fmc_generate_offsets reports, bit for bit.
+  const float tf = -1.3862943611f * __log2f(u);
+  const float rf = (tf > 0.0f) ? tf * rsqrtf(tf) : 0.0f;
+  float sf, cf;
+  __sincosf(6.2831853072f * ((float)b * 2.3283064365386963e-10f), &sf, &cf);
+  z0 = rf * cf;
+  z1 = rf * sf;
+  return;
+#endif
   const float t = -2.0f * ln_pos_normal(u);                       // >= 0 (u <= 1)
 #if defined(__CUDA_ARCH__)
   const float r = (t > 0.0f) ? t * rsqrtf(t) : 0.0f;

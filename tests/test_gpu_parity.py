@@ -192,3 +192,22 @@ def test_non_converging_fits_are_averaged_like_any_other(fmc, oracle):
     print("\n[stress] rc histogram gpu %s oracle %s ; fits agreeing to 1e-5: %.3f"
           % (got["rc_count"][3:11], want["rc_count"][3:11], same.mean()))
     assert same.mean() > 0.9
+
+
+def test_in_process_multi_gpu_split_equals_one_gpu(fmc, oracle):
+    """fmc_bootstrap_run(ngpus=G): contiguous id ranges on G devices, one host thread each,
+    accumulator blocks added on the host.  Same fits, sums equal up to summation order."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    model, x, y, err = datasets.dataset("c1")
+    start = _start(oracle, model, x, y, err)
+    n = 20001
+    one = fmc.monte_carlo_fit_data(x, y, err, model, nrand_points=n, ngpus=1, params_init=start, initial_fit=False,
+                                   per_resample=True)
+    two = fmc.monte_carlo_fit_data(x, y, err, model, nrand_points=n, ngpus=2, params_init=start, initial_fit=False,
+                                   per_resample=True)
+    assert np.array_equal(one["params"], two["params"])
+    assert np.allclose(one["sum_p"], two["sum_p"], rtol=1e-12) and np.allclose(one["sum_p2"], two["sum_p2"], rtol=1e-12)
+    assert np.array_equal(one["rc_count"], two["rc_count"])
