@@ -272,10 +272,14 @@ def main():
                        "wall_s_timed_region": t_wall},
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(8 * (3 * NDATA + p)),
                     "d2h_bytes_per_step": int(8 * ctx.accumulator_len())},
-            "gpu_launches": 4 * args.steps * world,  # init_pass + iterate kernels for each of fit_data's two nl2sno calls
+            "gpu_launches": 5 * args.steps * world,  # jac0, init_shared, iterate, init_pass, iterate (fit_data = two nl2sno calls)
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": None,
+                         "frac": achieved / peak_tflops,
+                         # dram__bytes_read+write of the dominant kernel (iterate, first nl2sno call) per launch,
+                         # from profiles/r1_pipeline_ncu_summary.txt; algorithmic bytes are ~0.4 KB of pipeline
+                         # state per fit (0.4 GB per launch), the rest is the solver's thread-local state
+                         "traffic": 2.01e9,
                          "note": "FP64-FMA bound (SURVEY.md 8d), not hbm/tensor; peak = DFMA-chain microbenchmark "
                                  "measured in this run; achieved = %.0f algorithmic flops/fit x kernel fits/s" % w_fit},
         }
