@@ -36,9 +36,6 @@ namespace fmc {
 #ifndef FMC_MIN_BLOCKS
 #define FMC_MIN_BLOCKS 1
 #endif
-#ifndef FMC_ROWS_PER_ITER
-#define FMC_ROWS_PER_ITER 4  // data points per trip of the pass loop (4 or 2)
-#endif
 #ifndef FMC_PHILOX_ROUNDS
 #define FMC_PHILOX_ROUNDS 10
 #endif
@@ -91,27 +88,7 @@ FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, in
                                      const double* __restrict__ zrow,
                                      const PassPoint<M::NPARAM>& pa, const PassPoint<M::NPARAM>& pb,
                                      PassAcc<M::NPARAM>& acc) {
-#if FMC_ROWS_PER_ITER == 4 && defined(FMC_PIPELINE_RNG)
-  // software-pipelined generator: the deviates of the NEXT four points are produced while the
-  // FP64 work of the current four is in flight (independent instruction streams in one body)
-  float zn[4] = {0.f, 0.f, 0.f, 0.f};
-  if (!INJECT) normals4(seed, id, 0u, zn);
-  for (int i = 0; i < n_pad; i += 4) {
-    float z[4] = {zn[0], zn[1], zn[2], zn[3]};
-    if (!INJECT) normals4(seed, id, (uint32_t)((i >> 2) + 1), zn);
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const RowData rd = rows[i + m];
-      double zz;
-      if (INJECT)
-        zz = (i + m < n) ? zrow[i + m] : 0.0;
-      else
-        zz = (double)z[m];
-      const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
-      row_accumulate<M, WITH_B>(pa, pb, rd.x, yfit, rd.rerr, acc);
-    }
-  }
-#elif FMC_ROWS_PER_ITER == 4
+  // four data points per trip: one counter block of the generator yields their four deviates
   for (int i = 0; i < n_pad; i += 4) {
     float z[4];
     if (!INJECT) normals4(seed, id, (uint32_t)(i >> 2), z);
@@ -127,28 +104,6 @@ FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, in
       row_accumulate<M, WITH_B>(pa, pb, rd.x, yfit, rd.rerr, acc);
     }
   }
-#else
-  // two data points per trip (lower register pressure); the generator still yields four
-  // deviates per counter block, the second pair is carried to the next trip
-  float z[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-  for (int i = 0; i < n_pad; i += 2) {
-    const bool second = (i & 2) != 0;
-    if (!INJECT && !second) normals4(seed, id, (uint32_t)(i >> 2), z);
-    const float zp[2] = {second ? z[2] : z[0], second ? z[3] : z[1]};
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const RowData rd = rows[i + m];
-      double zz;
-      if (INJECT)
-        zz = (i + m < n) ? zrow[i + m] : 0.0;
-      else
-        zz = (double)zp[m];
-      const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
-      row_accumulate<M, WITH_B>(pa, pb, rd.x, yfit, rd.rerr, acc);
-    }
-  }
-#endif
 }
 
 template <bool SMEM>
@@ -168,10 +123,7 @@ FMC_INLINE __device__ const RowData* stage_rows(const KernelArgs& a, unsigned ch
 // none needs the J(x0)^T r(x) part, so this stage runs as its own, perfectly uniform kernel:
 // one fit per thread, static assignment, no solver code.
 template <class M, bool INJECT, bool SMEM>
-#ifndef FMC_INIT_MIN_BLOCKS
-#define FMC_INIT_MIN_BLOCKS 1
-#endif
-__global__ void __launch_bounds__(FMC_THREADS, FMC_INIT_MIN_BLOCKS) init_pass_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int PP = P * (P + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
