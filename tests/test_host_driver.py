@@ -128,7 +128,7 @@ def test_fitter_mc_transcript_on_the_probe_file(tmp_path, oracle):
     assert np.isclose(chi[1], 1.3016073130752277, rtol=1e-10)
     q = [float(v) for v in re.findall(r"this bad =\s+([-0-9.E+]+)", t)]
     assert np.isclose(q[1], 0.10353124942978763, rtol=1e-8)
-    mc = re.findall(r"Parameter (\S+)\s+=\s+([-0-9.E+]+) \+/-\s+([-0-9.E+]+)", t)
+    mc = re.findall(r"Parameter (\S+)\s+=\s+([-0-9.E+]+)\s+\+/-\s+([-0-9.E+]+)", t)
     assert [m[0] for m in mc] == ["a", "b", "al"]
     want_m, want_s = [0.50388, 1.96112, 1.28296], [0.01247, 0.03474, 0.04703]   # mcfit.py, 2000 samples
     for (_, mean, sd), wm, ws in zip(mc, want_m, want_s):
