@@ -151,6 +151,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("FMC_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack if a run stalls
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["FMC_BENCH_WATCHDOG"]), repeat=False, exit=True)
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -203,48 +207,51 @@ def main():
         ctx.wait()
         return e0.elapsed_time(e1)
 
+    sync_token = torch.zeros(1, dtype=torch.float64, device=dev)
+
     def sync_all():
+        """barrier + device synchronize (the barrier is a 1-element all-reduce on the working stream)"""
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(sync_token)
         torch.cuda.synchronize()
 
     for w in range(args.warmup):
         device_step(w)
-    peak_tflops, _ = fmc.measure_dfma_peak(local_rank, 20000)
 
     sampler = ClockSampler(local_rank)
     sync_all()
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     t_wall0 = time.perf_counter()
     ms = [device_step(args.warmup + k) for k in range(args.steps)]
     sync_all()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     dev_ms = float(sum(ms))
     kernel_ms = ctx.kernel_ms()
     last = fmc.decode_accumulator(MODEL, start, acc.cpu().numpy())
+    n_anomalies = ctx.anomalies()[2]  # fits of the last step that hit a solver safety cap (normally 0)
 
-    # ---- e2e: public host API, host buffers, H2D + D2H inside the timed region
-    ctx.set_accumulator_dev(0)
-    ctx.set_stream(0)
-
+    # ---- e2e: public host API with HOST buffers; per step the inputs go host->device and the
+    # (all-reduced) accumulator block comes back device->host, all inside the timed region and
+    # all on the one stream that also carries the kernels and the collective.
     def e2e_step(step_no):
-        ctx.set_data(MODEL, x, y, err)  # H2D of the step's inputs
-        ctx.launch(start, nres, seed=SEED, first_counter=(step_no * world + rank) * nres)
-        out = ctx.finish()              # D2H of the accumulator block
-        if world > 1:
-            t = torch.from_numpy(np.concatenate([out["sum_p"], out["sum_p2"], out["sum_prop"], out["sum_prop2"]])).to(dev)
-            dist.all_reduce(t)
-            t.cpu()
-        return out
+        ctx.set_data(MODEL, x, y, err)              # H2D of the step's inputs (x, y, err)
+        ctx.launch(start, nres, seed=SEED, first_counter=(step_no * world + rank) * nres)  # H2D of params_start
+        fdist.allreduce_accumulator(acc)
+        host_block = acc.cpu()                      # D2H of the result block (synchronises)
+        ctx.wait()
+        return host_block
 
     e2e_step(1000)
     sync_all()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        e2e_step(2000 + k)
+        last_block = e2e_step(2000 + k)
     sync_all()
     e2e_s = time.perf_counter() - t0
+    e2e_check = fmc.decode_accumulator(MODEL, start, last_block.numpy())
+    assert e2e_check["nfit"] == nres * world, (e2e_check["nfit"], nres, world)
 
     # max over ranks
     if world > 1:
@@ -254,8 +261,13 @@ def main():
     total_fits = float(nres) * args.steps * world
     value = total_fits / (dev_ms * 1e-3)
     e2e_value = total_fits / e2e_s
+    if world > 1:
+        sync_all()
+        dist.destroy_process_group()
 
     if rank == 0:
+        # FP64 roofline denominator: DFMA-chain microbenchmark on this GPU, after the timed work
+        peak_tflops, _ = fmc.measure_dfma_peak(local_rank, 20000)
         tot = last["totals"].astype(float) / max(last["nfit"], 1)
         F, G = tot[0], tot[1]
         A = max(G - 2.0, 0.0)
@@ -269,7 +281,7 @@ def main():
             "config": {"workload": WORKLOAD, "resamples_per_gpu_per_step": nres, "seed": SEED,
                        "l2": "flushed between steps (256 MiB memset); working set (32 KB) lives in shared memory",
                        "geometry": ctx.geometry(), "per_fit": {"nfcall": F, "ngcall": G, "niter": tot[2], "passes": tot[3]},
-                       "wall_s_timed_region": t_wall},
+                       "wall_s_timed_region": t_wall, "solver_safety_cap_hits_last_step": int(n_anomalies)},
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(8 * (3 * NDATA + p)),
                     "d2h_bytes_per_step": int(8 * ctx.accumulator_len())},
             "gpu_launches": 5 * args.steps * world,  # jac0, init_shared, iterate, init_pass, iterate (fit_data = two nl2sno calls)
@@ -295,9 +307,6 @@ def main():
                                     "sample": "%d resamples of the C2 workload, reference-equivalent cost "
                                               "(serial RANLUX, covariance, Jacobian copies, histogram)" % sample}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

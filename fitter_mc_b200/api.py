@@ -68,6 +68,7 @@ def lib():
     L.fmc_launch.argtypes = [C.c_void_p, _dp, C.c_longlong, C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_int]
     L.fmc_finish.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _lp, _lp]
     L.fmc_wait.argtypes = [C.c_void_p]
+    L.fmc_last_anomalies.argtypes = [C.c_void_p, _lp, _ip, C.c_int]
     L.fmc_decode_accumulator.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _lp, _lp, _lp]
     L.fmc_last_kernel_ms.restype = C.c_float
     L.fmc_last_kernel_ms.argtypes = [C.c_void_p]
@@ -268,6 +269,15 @@ class Context:
 
     def wait(self):
         _check(lib().fmc_wait(self._h), "fmc_wait")
+
+    def anomalies(self):
+        """(ids, flags) of fits of the last launch that hit a solver safety cap (normally none)."""
+        ids = np.zeros(64, dtype=np.int64)
+        flags = np.zeros(64, dtype=np.int32)
+        n = lib().fmc_last_anomalies(self._h, ids.ctypes.data_as(_lp), flags.ctypes.data_as(_ip), 64)
+        if n < 0:
+            raise FmcError(n, "fmc_last_anomalies")
+        return ids[:min(n, 64)], flags[:min(n, 64)], n
 
     def kernel_ms(self):
         return float(lib().fmc_last_kernel_ms(self._h))

@@ -49,6 +49,7 @@ struct __align__(16) RowData {  // one data point, 32 B: two 16-byte broadcast l
 //   then ACC_NFIT, ACC_RC+0..15 (histogram of the 2nd-pass return code), ACC_NFCALL,
 //   ACC_NGCALL, ACC_NITER, ACC_NPASS.
 enum { ACC_NFIT = 0, ACC_RC = 1, ACC_NFCALL = 17, ACC_NGCALL = 18, ACC_NITER = 19, ACC_NPASS = 20, ACC_NTAIL = 21 };
+enum { ANOM_CAP = 64 };  // anomaly log: [0] count, then (id, flags) pairs
 FMC_HD inline int acc_len(int p, int q) { return 2 * (p + q) + ACC_NTAIL; }
 
 struct KernelArgs {
@@ -71,6 +72,7 @@ struct KernelArgs {
   double* props_out;        // optional [nres][Q]
   int* counters_out;        // optional [nres][10]
   unsigned long long* next_id;  // work counter of this launch, zeroed beforehand
+  unsigned long long* anom;     // anomaly log (fits that hit a safety cap), zeroed per launch
   double* acc;              // accumulator block, zeroed before the first chunk
 };
 
@@ -281,6 +283,14 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
 
   // end of an nl2sno call: hand the state to the next stage, or (second call) to the sums
   auto finish_call = [&]() {
+    if (s.anomaly != 0 && a.anom != nullptr) {
+      const unsigned long long kk = atomicAdd(a.anom, 1ULL);
+      if (kk < (unsigned long long)ANOM_CAP) {
+        a.anom[1 + 2 * kk] = (unsigned long long)(a.first + slot);
+        a.anom[2 + 2 * kk] = (unsigned long long)(s.anomaly | (a.call << 8));
+      }
+      s.anomaly = 0;
+    }
     if (a.call == 0) {
 #pragma unroll
       for (int i = 0; i < P; ++i) a.xbuf[i * a.cap + slot] = s.x[i];
@@ -378,7 +388,13 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
       pass_loop<M, INJECT, true>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
       pass_finish<P>(acc, s);
       ++fit_passes;
-      if (!s.resume()) {
+      bool more = s.resume();
+      if (more && fit_passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
+        s.anomaly |= 8;
+        s.rc = 9;
+        more = false;
+      }
+      if (!more) {
         finish_call();
         fetch();
       }

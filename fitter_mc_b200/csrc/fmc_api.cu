@@ -117,6 +117,7 @@ struct fmc_context {
   int chunk_p = 0;
   unsigned long long* counters_dev = nullptr;  // one work counter per iterate launch
   double* rowj_dev = nullptr;  // [n_pad][1+P] shared Jacobian rows at params_start + [PP] G0
+  unsigned long long* anom_dev = nullptr;  // anomaly log of the last launch
   long long rowj_cap = 0;
   int ncounters = 0;
   long long inflight = -1;
@@ -213,6 +214,8 @@ int fmc_create(fmc_context** out, int device) {
   c->acc_n = acc_len(FMC_MAX_PARAM, FMC_MAX_PARAM);
   FMC_CUDA(cudaMalloc(&c->acc_own, sizeof(double) * c->acc_n));
   c->acc = c->acc_own;
+  FMC_CUDA(cudaMalloc(&c->anom_dev, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP)));
+  FMC_CUDA(cudaMemset(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP)));
   *out = c;
   return FMC_OK;
 }
@@ -229,6 +232,7 @@ int fmc_destroy(fmc_context* c) {
   cudaFree(c->cnt);
   cudaFree(c->counters_dev);
   cudaFree(c->rowj_dev);
+  cudaFree(c->anom_dev);
   cudaFree(c->params_out_dev);
   cudaFree(c->props_out_dev);
   cudaFree(c->counters_dev_out);
@@ -375,6 +379,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   a.istate = c->istate;
   a.cnt = c->cnt;
   a.acc = c->acc;
+  a.anom = c->anom_dev;
 
   // data in shared memory when it fits (227 KB opt-in on B200), else through L1/L2
   size_t shmem = sizeof(RowData) * (size_t)c->n_pad;
@@ -411,6 +416,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
 
   if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 2 * nchunks, c->stream));
   FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
+  FMC_CUDA(cudaMemsetAsync(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP), c->stream));
   FMC_CUDA(cudaEventRecord(c->ev0, c->stream));
   if (shared_init && nresample > 0) FMC_CUDA(m.launch_jac0(a, c->rowj_dev, g0_dev, c->stream));
   for (long long ch = 0; ch < nchunks; ++ch) {
@@ -516,6 +522,19 @@ int fmc_wait(fmc_context* c) {
   FMC_CUDA(cudaStreamSynchronize(c->stream));
   c->inflight = -1;
   return FMC_OK;
+}
+
+int fmc_last_anomalies(fmc_context* c, long long* ids, int* flags, int cap) {
+  if (!c) return FMC_ERR_BAD_ARG;
+  FMC_CUDA(cudaSetDevice(c->device));
+  unsigned long long h[1 + 2 * fmc::ANOM_CAP];
+  FMC_CUDA(cudaMemcpy(h, c->anom_dev, sizeof(h), cudaMemcpyDeviceToHost));
+  const int n = (int)h[0];
+  for (int i = 0; i < n && i < cap && i < fmc::ANOM_CAP; ++i) {
+    if (ids) ids[i] = (long long)h[1 + 2 * i];
+    if (flags) flags[i] = (int)h[2 + 2 * i];
+  }
+  return n;
 }
 
 float fmc_last_kernel_ms(fmc_context* c) {

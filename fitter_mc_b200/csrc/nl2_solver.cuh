@@ -176,6 +176,11 @@ struct Nl2 {
   int ipivot[P];
   int ierr, irc, mlstgd, model, nfcall, nfgcal, radinc, restor, stage, swtch, toobig, xirc, cnvcod,
       kagqt, kalm, niter, ngcall, sused, hvalid, stpmod, phase, x_is_eval, rc, lsvmin_ix;
+  // Safety net for a massively parallel run: a fit must never spin forever.  Each bit records a
+  // loop that hit its (generous) cap; the fit then ends like a false convergence.  The caps are
+  // far above anything the reference's own bounds (kalim = 12 / 50, mxfcal, mxiter) allow in
+  // exact arithmetic, so they only bite on non-finite or inconsistent intermediate values.
+  int anomaly;
 
   // ------------------------------------------------------------------ entry points
   // Per-fit reset of the state that the reference leaves to persist between fits
@@ -183,6 +188,7 @@ struct Nl2 {
   FMC_HD void reset_fit() {
     mlstgd = 0;
     lsvmin_ix = 2;
+    anomaly = 0;
   }
 
   // nl2sno fresh start (toms573.f90:688-700): D = 1 for the first finite-difference Jacobian.
@@ -631,6 +637,7 @@ FMC_HD void Nl2<P>::lmstep() {
   double a, adi, alphak, b, dfacsq, dst, dtol, d1, d2, lk, oldphi, phi, phimax, phimin, psifac, rad,
       si, sj, sqrtak, t, twopsi, uk, wl;
   const double dfac = 256.0, ttol = 2.5, p001 = 1e-3;
+  int nloop = 0;
 
   psifac = 0.0;
   alphak = 0.0;
@@ -694,6 +701,10 @@ L50:
   if (uk <= 0.0) goto L330;
   alphak = fabs(v[STPPAR]) * v[RAD0] / rad;
 L70:
+  if (++nloop > 100) {  // safety cap (the reference relies on kalim = ka + 12)
+    anomaly |= 1;
+    goto L370;
+  }
   ka = ka + 1;
   for (i = 0; i < pp1o2; ++i) ww[rmat + i] = hmat[i];
   for (i = 0; i < p; ++i) ww[res + i] = qtr[i];
@@ -941,6 +952,7 @@ FMC_HD void Nl2<P>::gqtstp() {
   bool restrt;
   const double epsfac = 50.0, kappa = 2.0, p001 = 1e-3;
   const double dgxfac = epsfac * k::machep;
+  int nloop = 0;
 
   dst = 0.0;
   phi = 0.0;
@@ -1099,6 +1111,10 @@ L60:
   ww[phipin] = dst / t / t;
   lk = fmax(lk, phi * ww[phipin]);
 L200:
+  if (++nloop > 150) {  // safety cap (the reference relies on kalim = ka + 50)
+    anomaly |= 2;
+    goto L270;
+  }
   ka = ka + 1;
   if (-v[DST0] >= alphak || alphak < lk || alphak >= uk) alphak = uk * fmax(p001, sqrt(lk / uk));
   kk = 0;
@@ -1243,7 +1259,7 @@ L430:
 // ----------------------------------------------------------------- nl2itr, resumable
 template <int P>
 FMC_HD bool Nl2<P>::resume() {
-  int l;
+  int l, spins = 0;
   double e, sttsst, t, t1;
 
   if (phase == PH_JAC) goto L385;
@@ -1295,6 +1311,11 @@ L160:
   }
 
 L180:
+  if (++spins > 40) {  // safety cap: step recomputed over and over without a new evaluation
+    anomaly |= 4;
+    rc = 8;
+    return false;
+  }
   if (model == 2) goto L220;
   if (kalm < 0) factor();
   if (!hvalid) {

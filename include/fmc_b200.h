@@ -123,6 +123,11 @@ int fmc_wait(fmc_context* ctx);
 int fmc_decode_accumulator(int model, const double* params_start, const double* acc_host,
                            double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,
                            long long* nfit, long long* rc_count, long long* totals);
+/* Fits of the last launch whose solver hit one of its safety caps (a fit may never spin forever
+ * on the GPU; such a fit ends like a false convergence).  Returns their number (0 in any normal
+ * run) and fills up to `cap` global resample ids and flag words (bit0 lmstep, bit1 gqtstp, bit2
+ * step recomputation, bit3 passes; bits 8+ = which nl2sno call).  Call after fmc_finish/fmc_wait. */
+int fmc_last_anomalies(fmc_context* ctx, long long* ids, int* flags, int cap);
 /* Device time of the last fit kernel (CUDA events on the launching stream), milliseconds. */
 float fmc_last_kernel_ms(fmc_context* ctx);
 /* Grid geometry chosen for the last launch: blocks, threads per block, blocks per SM, SMs. */
