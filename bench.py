@@ -43,6 +43,7 @@ RESAMPLES = 1_000_000  # per GPU per step (BASELINE.json configs[1])
 SEED = 31415
 WORKLOAD = "C2: model test4 y=a+b*exp(-al*x)+c*x (p=4, nprop=1), ndata=1000, 1e6 resamples per GPU per step"
 C_T = 20  # flops per transcendental, fixed by SURVEY.md section 8d
+RESULT_OUT = sys.stdout
 
 
 def make_problem():
@@ -127,7 +128,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     desc = "%d resamples/step of the C2 workload, serial RANLUX+polar stream, covariance+Jacobian-copy+histogram cost kept" % sample
-    print(json.dumps({
+    RESULT_OUT.write(json.dumps({
         "impl": "reference", "metric": "bootstrap fits/sec (ndata=1000, 4 params)", "value": value, "unit": "fits/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -135,7 +136,8 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }) + "\n")
+    RESULT_OUT.flush()
 
 
 def main():
@@ -151,6 +153,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # The contract is ONE JSON line on stdout.  Libraries chat on fd 1 (NCCL prints its version
+    # banner there), so keep the real stdout aside for the result line and send the rest to stderr.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if os.environ.get("FMC_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack if a run stalls
         import faulthandler
 
@@ -306,7 +314,8 @@ def main():
             line["cpu_baseline"] = {"value": sample / dt, "unit": "fits/s", "cores": cores, "kind": "port",
                                     "sample": "%d resamples of the C2 workload, reference-equivalent cost "
                                               "(serial RANLUX, covariance, Jacobian copies, histogram)" % sample}
-        print(json.dumps(line))
+        RESULT_OUT.write(json.dumps(line) + "\n")
+        RESULT_OUT.flush()
 
 
 if __name__ == "__main__":
