@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
   __syncthreads();
 
   Nl2<P> s;
+  s.anomaly = 0;
   double msum[NM], mcmp[NM];
 #pragma unroll
   for (int i = 0; i < NM; ++i) {
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
         for (int i = 0; i < P; ++i) xs[i] = a.xbuf[i * a.cap + slot];
         s.mlstgd = a.istate[slot];
         s.lsvmin_ix = a.istate[a.cap + slot];
+        s.anomaly = 0;
       }
       s.begin(xs);
       s.res_f = a.init[slot];

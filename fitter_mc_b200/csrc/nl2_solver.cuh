@@ -953,6 +953,7 @@ FMC_HD void Nl2<P>::gqtstp() {
   const double epsfac = 50.0, kappa = 2.0, p001 = 1e-3;
   const double dgxfac = epsfac * k::machep;
   int nloop = 0;
+  bool have_q = kagqt >= 0;  // w(q) holds a solved step (of an earlier call for this H, or of this one)
 
   dst = 0.0;
   phi = 0.0;
@@ -1019,6 +1020,7 @@ L50:
   ltsolve(p, &ww[q], lmat, dig);
   v[NREDUC] = 0.5 * dotn(p, &ww[q], &ww[q]);
   ltsolve_t(p, &ww[q], lmat, &ww[q]);
+  have_q = true;
   dst = nrm2(p, &ww[q]);
   v[DST0] = dst;
   phi = dst - rad;
@@ -1113,7 +1115,8 @@ L60:
 L200:
   if (++nloop > 150) {  // safety cap (the reference relies on kalim = ka + 50)
     anomaly |= 2;
-    goto L270;
+    if (have_q) goto L270;  // keep the last step that was actually solved for ...
+    goto L430;              // ... or take no step at all
   }
   ka = ka + 1;
   if (-v[DST0] >= alphak || alphak < lk || alphak >= uk) alphak = uk * fmax(p001, sqrt(lk / uk));
@@ -1137,6 +1140,7 @@ L200:
 L230:
   ltsolve(p, &ww[q], lmat, dig);
   ltsolve_t(p, &ww[q], lmat, &ww[q]);
+  have_q = true;
   dst = nrm2(p, &ww[q]);
   phi = dst - rad;
   if (phi <= phimax && phi >= phimin) goto L270;
