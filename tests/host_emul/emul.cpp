@@ -38,7 +38,7 @@ void run_pass(Nl2<M::NPARAM>& s, int n, const double* x, const double* yfit, con
 // counters[pass][0..3] = rc, nfcall, ngcall, niter ; counters[pass][4] = passes over the data
 template <class M>
 int fit_one(int n, const double* x, const double* yfit, const double* err, double* params,
-            int* counters) {
+            int* counters, int* anomaly_out = nullptr) {
   constexpr int P = M::NPARAM;
   std::vector<double> rerr(n);
   for (int i = 0; i < n; ++i) rerr[i] = 1.0 / err[i];
@@ -52,7 +52,13 @@ int fit_one(int n, const double* x, const double* yfit, const double* err, doubl
       run_pass<M>(s, n, x, yfit, rerr.data());
       ++npass;
       if (!s.resume()) break;
+      if (npass > 2 * (k::mxfcal + k::mxiter)) {  // the kernel's cap on passes per call
+        s.anomaly |= 8;
+        s.rc = 9;
+        break;
+      }
     }
+    if (anomaly_out) *anomaly_out |= s.anomaly << (8 * pass);
     for (int i = 0; i < P; ++i) params[i] = s.x[i];
     if (counters) {
       int* c = counters + 5 * pass;
@@ -69,7 +75,7 @@ int fit_one(int n, const double* x, const double* yfit, const double* err, doubl
 template <class M>
 int bootstrap(int n, const double* x, const double* y, const double* err, const double* start,
               long long nres, const double* z, unsigned long long seed, long long first,
-              double* params_out, double* props_out, int* counters_out) {
+              double* params_out, double* props_out, int* counters_out, int* anomalies_out = nullptr) {
   constexpr int P = M::NPARAM, Q = M::NPROP;
   std::vector<double> yfit(n), p(P);
   for (long long r = 0; r < nres; ++r) {
@@ -83,7 +89,9 @@ int bootstrap(int n, const double* x, const double* y, const double* err, const 
       }
     }
     for (int i = 0; i < P; ++i) p[i] = start[i];
-    fit_one<M>(n, x, yfit.data(), err, p.data(), counters_out ? counters_out + 10 * r : nullptr);
+    int anom = 0;
+    fit_one<M>(n, x, yfit.data(), err, p.data(), counters_out ? counters_out + 10 * r : nullptr, &anom);
+    if (anomalies_out) anomalies_out[r] = anom;
     std::memcpy(params_out + (size_t)r * P, p.data(), sizeof(double) * P);
     if (props_out) M::derived_properties(p.data(), props_out + (size_t)r * Q);
   }
@@ -123,16 +131,23 @@ int emul_fit(int model, int n, const double* x, const double* yfit, const double
   return -1;
 }
 
+int emul_bootstrap2(int model, int n, const double* x, const double* y, const double* err,
+                    const double* start, long long nres, const double* z, unsigned long long seed,
+                    long long first, double* params_out, double* props_out, int* counters_out,
+                    int* anomalies_out) {
+  switch (model) {
+    case 0: return bootstrap<ModelUser>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out, anomalies_out);
+    case 1: return bootstrap<ModelTest4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out, anomalies_out);
+    case 2: return bootstrap<ModelPeaks10>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out, anomalies_out);
+    case 3: return bootstrap<ModelStiff4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out, anomalies_out);
+  }
+  return -1;
+}
+
 int emul_bootstrap(int model, int n, const double* x, const double* y, const double* err,
                    const double* start, long long nres, const double* z, unsigned long long seed,
                    long long first, double* params_out, double* props_out, int* counters_out) {
-  switch (model) {
-    case 0: return bootstrap<ModelUser>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
-    case 1: return bootstrap<ModelTest4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
-    case 2: return bootstrap<ModelPeaks10>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
-    case 3: return bootstrap<ModelStiff4>(n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out);
-  }
-  return -1;
+  return emul_bootstrap2(model, n, x, y, err, start, nres, z, seed, first, params_out, props_out, counters_out, nullptr);
 }
 
 int emul_row_model(int model, const double* x, const double* h, double xi, double* m0, double* dm_engine,
