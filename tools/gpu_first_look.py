@@ -1,7 +1,7 @@
 """Scratch driver for the first GPU runs: DFMA peak, kernel geometry, throughput per model."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import fitter_mc_b200 as fmc
 import datasets, oracle_lib as oracle

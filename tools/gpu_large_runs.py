@@ -2,7 +2,7 @@
 C4 / C5 configs at sizes that fill the device.  Prints fits/s and ensemble statistics."""
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import fitter_mc_b200 as fmc
 import datasets, oracle_lib as oracle

@@ -1,7 +1,7 @@
 """Short single-kernel run of the headline config (C2: n=1000, p=4) for ncu captures."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import fitter_mc_b200 as fmc
 import datasets, oracle_lib as oracle
 

@@ -2,7 +2,7 @@
 and injection paths, per-resample outputs, ragged n, two chunks' worth of code paths."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import fitter_mc_b200 as fmc
 import datasets

@@ -1,7 +1,7 @@
 """Diagnostic: which part of the end-to-end step stalls with >= 4 NCCL ranks."""
 import os, sys, time, datetime, faulthandler
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch, torch.distributed as dist
 import fitter_mc_b200 as fmc
 import datasets, oracle_lib as oracle
