@@ -15,6 +15,8 @@ from .api import (  # noqa: F401
     finalise_moments,
     fit_data,
     generate_offsets,
+    histogram_quantiles,
+    histogram_range_from_pilot,
     initialise_model,
     lib,
     lib_path,

@@ -75,6 +75,16 @@ def lib():
     L.fmc_last_launch_geometry.argtypes = [C.c_void_p, _ip]
     L.fmc_measure_dfma_peak.argtypes = [C.c_int, C.c_int, _dp, C.POINTER(C.c_float)]
     L.fmc_finalise_moments.argtypes = [C.c_int, C.c_longlong, _dp, _dp, _dp, _dp]
+    L.fmc_bootstrap_run_binned.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, C.c_ulonglong,
+                                           C.c_longlong, C.c_int, _dp, _dp, _dp, _dp, _lp, _lp, C.c_int, _dp, _dp,
+                                           C.c_void_p]
+    L.fmc_set_histogram.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    L.fmc_histogram_len.restype = C.c_longlong
+    L.fmc_histogram_len.argtypes = [C.c_void_p]
+    L.fmc_set_histogram_dev.argtypes = [C.c_void_p, C.c_void_p]
+    L.fmc_get_histogram.argtypes = [C.c_void_p, C.c_void_p]
+    L.fmc_histogram_quantiles.restype = C.c_longlong
+    L.fmc_histogram_quantiles.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp, C.c_int, _dp]
     _lib = L
     return L
 
@@ -170,9 +180,16 @@ def decode_accumulator(model, params_start, acc):
 
 
 def monte_carlo_fit_data(x, y, err_y, model=0, nrand_points=100000, seed=DEFAULT_SEED, first_counter=0,
-                         ngpus=1, params_init=None, z_inject=None, per_resample=False, initial_fit=True):
+                         ngpus=1, params_init=None, z_inject=None, per_resample=False, initial_fit=True,
+                         histogram_bins=0, histogram_range=None, pilot=4096):
     """monte_carlo_fit_data, bootstrap.f90:253-362, without the printing: initial fit on the raw
-    data (288-295), the bootstrap loop (297-330, one C-ABI call), means and Bessel errors (328-341)."""
+    data (288-295), the bootstrap loop (297-330, one C-ABI call), means and Bessel errors (328-341).
+
+    histogram_bins > 0 is the large-N form of make_histogram (bootstrap.f90:301-325): every
+    parameter and property is binned on the device; the result gains `hist_counts`
+    [nparam + nprop][bins + 2], `hist_lo`, `hist_hi`.  Without histogram_range=(lo, hi) the range
+    is mean -/+ 8 sigma of a pilot of `pilot` resamples (ids taken from the end of the id space
+    so that they do not coincide with the run's own)."""
     info = initialise_model(model)
     p, q = info["nparam"], info["nprop"]
     x, y, err_y = map(_f64, (x, y, err_y))
@@ -190,16 +207,61 @@ def monte_carlo_fit_data(x, y, err_y, model=0, nrand_points=100000, seed=DEFAULT
     qout = np.zeros((n, max(q, 1))) if per_resample else None
     rcc = np.zeros(16, dtype=np.int64)
     tot = np.zeros(4, dtype=np.int64)
-    _check(lib().fmc_bootstrap_run(model, len(x), _d(x), _d(y), _d(err_y), _d(start), n, seed, first_counter, ngpus,
-                                   _d(zi), _d(s[0]), _d(s[1]), _d(s[2]), _d(s[3]), _d(pout), _d(qout),
-                                   rcc.ctypes.data_as(_lp), tot.ctypes.data_as(_lp)), "fmc_bootstrap_run")
+    hist = {}
+    if histogram_bins:
+        if zi is not None or per_resample:
+            raise ValueError("binned runs keep no per-resample arrays; bin those with distributed.bin_values")
+        nb = int(histogram_bins)
+        if histogram_range is None:
+            npilot = max(2, min(int(pilot), max(n, 2)))
+            pp, pq = np.zeros((npilot, p)), np.zeros((npilot, max(q, 1)))
+            dummy = [np.zeros(p), np.zeros(p), np.zeros(max(q, 1)), np.zeros(max(q, 1))]
+            _check(lib().fmc_bootstrap_run(model, len(x), _d(x), _d(y), _d(err_y), _d(start), npilot, seed,
+                                           (1 << 62) - npilot, 1, None, _d(dummy[0]), _d(dummy[1]), _d(dummy[2]),
+                                           _d(dummy[3]), _d(pp), _d(pq), None, None), "fmc_bootstrap_run (pilot)")
+            blo, bhi = histogram_range_from_pilot(np.column_stack([pp, pq[:, :q]]))
+        else:
+            blo, bhi = (_f64(v).copy() for v in histogram_range)
+        counts = np.zeros((p + q, nb + 2), dtype=np.uint64)
+        _check(lib().fmc_bootstrap_run_binned(model, len(x), _d(x), _d(y), _d(err_y), _d(start), n, seed,
+                                              first_counter, ngpus, _d(s[0]), _d(s[1]), _d(s[2]), _d(s[3]),
+                                              rcc.ctypes.data_as(_lp), tot.ctypes.data_as(_lp), nb, _d(blo), _d(bhi),
+                                              counts.ctypes.data_as(C.c_void_p)), "fmc_bootstrap_run_binned")
+        hist = dict(hist_counts=counts, hist_lo=blo, hist_hi=bhi)
+    else:
+        _check(lib().fmc_bootstrap_run(model, len(x), _d(x), _d(y), _d(err_y), _d(start), n, seed, first_counter,
+                                       ngpus, _d(zi), _d(s[0]), _d(s[1]), _d(s[2]), _d(s[3]), _d(pout), _d(qout),
+                                       rcc.ctypes.data_as(_lp), tot.ctypes.data_as(_lp)), "fmc_bootstrap_run")
     params_opt, err_params_opt = finalise_moments(n, s[0], s[1])
     props_opt, err_props_opt = finalise_moments(n, s[2][:q], s[3][:q])
-    return dict(info=info, params_fit=start, props_fit=derived_properties(model, start), rc_init=rc_init,
+    return dict(**hist, info=info, params_fit=start, props_fit=derived_properties(model, start), rc_init=rc_init,
                 params_opt=params_opt, err_params_opt=err_params_opt, props_opt=props_opt,
                 err_props_opt=err_props_opt, sum_p=s[0], sum_p2=s[1], sum_prop=s[2][:q], sum_prop2=s[3][:q],
                 params=pout, props=None if qout is None else qout[:, :q], rc_count=rcc, totals=tot,
                 nrand_points=n)
+
+
+def histogram_quantiles(counts, lo, hi, probs):
+    """Quantiles of one binned quantity (its nbins + 2 counts, fmc_b200.h).  Returns
+    (quantiles, number of resamples outside [lo, hi))."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    probs = _f64(np.atleast_1d(probs))
+    out = np.zeros(len(probs))
+    outside = lib().fmc_histogram_quantiles(counts.ctypes.data_as(C.c_void_p), len(counts) - 2, float(lo), float(hi),
+                                            _d(probs), len(probs), _d(out))
+    if outside < 0:
+        raise FmcError(-4, "fmc_histogram_quantiles")
+    return out, int(outside)
+
+
+def histogram_range_from_pilot(values, nsigma=8.0):
+    """[lo, hi) per column from a pilot sample of per-resample results: mean -/+ nsigma standard
+    deviations (a degenerate column gets a unit-width range round its value)."""
+    v = np.asarray(values, dtype=np.float64)
+    v = v[np.all(np.isfinite(v), axis=1)]
+    m, sd = v.mean(axis=0), v.std(axis=0)
+    sd = np.where(sd > 0, sd, 0.5 / nsigma)
+    return m - nsigma * sd, m + nsigma * sd
 
 
 def measure_dfma_peak(device=0, iters=20000):
@@ -269,6 +331,31 @@ class Context:
 
     def wait(self):
         _check(lib().fmc_wait(self._h), "fmc_wait")
+
+    def set_histogram(self, nbins, lo=None, hi=None):
+        """Bin every fitted parameter and property on the device (replaces histogram_<prop>.dat,
+        bootstrap.f90:319-325).  lo/hi: [nparam + nprop], parameters first.  nbins=0: off."""
+        if nbins:
+            lo, hi = _f64(lo), _f64(hi)
+            k = self.info["nparam"] + self.info["nprop"]
+            if lo.shape != (k,) or hi.shape != (k,):
+                raise ValueError("lo and hi need nparam + nprop = %d entries" % k)
+        _check(lib().fmc_set_histogram(self._h, int(nbins), _d(lo) if nbins else None, _d(hi) if nbins else None),
+               "fmc_set_histogram")
+        self._hist = (int(nbins), lo, hi) if nbins else None
+
+    def histogram_len(self):
+        return int(lib().fmc_histogram_len(self._h))
+
+    def set_histogram_dev(self, ptr):
+        _check(lib().fmc_set_histogram_dev(self._h, C.c_void_p(ptr)), "fmc_set_histogram_dev")
+
+    def histogram(self):
+        """Counts of the last launch on this GPU, uint64 [nparam + nprop][nbins + 2]."""
+        nbins = self._hist[0]
+        out = np.zeros((self.histogram_len() // (nbins + 2), nbins + 2), dtype=np.uint64)
+        _check(lib().fmc_get_histogram(self._h, out.ctypes.data_as(C.c_void_p)), "fmc_get_histogram")
+        return out
 
     def anomalies(self):
         """(ids, flags) of fits of the last launch that hit a solver safety cap (normally none)."""

@@ -50,6 +50,7 @@ struct __align__(16) RowData {  // one data point, 32 B: two 16-byte broadcast l
 //   ACC_NGCALL, ACC_NITER, ACC_NPASS.
 enum { ACC_NFIT = 0, ACC_RC = 1, ACC_NFCALL = 17, ACC_NGCALL = 18, ACC_NITER = 19, ACC_NPASS = 20, ACC_NTAIL = 21 };
 enum { ANOM_CAP = 64 };  // anomaly log: [0] count, then (id, flags) pairs
+enum { HIST_MAX_QUANT = 32 };  // binned quantities: P parameters then Q properties
 FMC_HD inline int acc_len(int p, int q) { return 2 * (p + q) + ACC_NTAIL; }
 
 struct KernelArgs {
@@ -75,6 +76,30 @@ struct KernelArgs {
   unsigned long long* anom;     // anomaly log (fits that hit a safety cap), zeroed per launch
   double* acc;              // accumulator block, zeroed before the first chunk
 };
+
+// Optional binned distributions of the fitted parameters and properties (replaces the
+// reference's one-text-line-per-resample histogram files, bootstrap.f90:319-325): quantity j
+// has `bins` equal-width bins on [lo[j], lo[j] + bins / scale[j]), stored as
+// hist[j * (bins + 2) + b] with b = 0 underflow (and NaN), 1..bins, bins + 1 overflow.
+struct HistArgs {
+  unsigned long long* hist;
+  int bins;
+  int np, nq;                // parameters, properties per fit
+  const double* params;      // [nres][np]  fitted parameters of one chunk
+  const double* props;       // [nres][nq]
+  long long nres;
+  double lo[HIST_MAX_QUANT];
+  double scale[HIST_MAX_QUANT];
+};
+
+// Bin index of value v: the same three FP64 operations (subtract, multiply, truncate) on host
+// and device, so a host re-binning of per-resample outputs reproduces the counts exactly.
+FMC_HD inline int hist_bin(double v, double lo, double scale, int nbins) {
+  const double t = (v - lo) * scale;
+  if (!(t >= 0.0)) return 0;
+  if (t >= (double)nbins) return nbins + 1;
+  return 1 + (int)t;
+}
 
 FMC_INLINE __device__ void kahan_add(double& s, double& c, double v) {
   const double y = v - c;

@@ -1,6 +1,7 @@
 // C ABI of libfmc_b200.so (declared in include/fmc_b200.h).  Host-side plumbing only:
 // device buffers, stream, launch geometry, decoding of the accumulator block.  All the
 // arithmetic of the hot path is in bootstrap_kernel.cuh / nl2_solver.cuh / pass_eval.cuh.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -89,6 +90,26 @@ __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// Binning runs as its own small kernel over the per-fit results of a chunk, so that the fit
+// kernels are the same machine code whether or not distributions are requested.  Traffic:
+// 8 (P+Q) B read per fit and one 64-bit reduction per quantity -- three orders of magnitude
+// below the fit kernels' time.  Counts are integers: the result does not depend on the order
+// in which fits are binned or GPUs are summed.
+__global__ void __launch_bounds__(256) hist_kernel(const fmc::HistArgs h) {
+  const int nquant = h.np + h.nq;
+  const long long total = h.nres * nquant;
+  const int stride = h.bins + 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    // element e of the concatenation [params | props]: consecutive threads read consecutive doubles
+    const bool is_param = e < h.nres * h.np;
+    const long long idx = is_param ? e : e - h.nres * h.np;
+    const int j = is_param ? (int)(idx % h.np) : h.np + (int)(idx % h.nq);
+    const double v = is_param ? h.params[idx] : h.props[idx];
+    atomicAdd(h.hist + (size_t)j * stride + fmc::hist_bin(v, h.lo[j], h.scale[j], h.bins), 1ULL);
+  }
+}
+
 }  // namespace
 
 struct fmc_context {
@@ -118,6 +139,12 @@ struct fmc_context {
   unsigned long long* counters_dev = nullptr;  // one work counter per iterate launch
   double* rowj_dev = nullptr;  // [n_pad][1+P] shared Jacobian rows at params_start + [PP] G0
   unsigned long long* anom_dev = nullptr;  // anomaly log of the last launch
+  unsigned long long* hist_own = nullptr;  // binned distributions (optional)
+  unsigned long long* hist = nullptr;
+  long long hist_own_cap = 0;
+  int hist_bins = 0;
+  double hist_lo[fmc::HIST_MAX_QUANT] = {0};
+  double hist_scale[fmc::HIST_MAX_QUANT] = {0};
   long long rowj_cap = 0;
   int ncounters = 0;
   long long inflight = -1;
@@ -233,6 +260,7 @@ int fmc_destroy(fmc_context* c) {
   cudaFree(c->counters_dev);
   cudaFree(c->rowj_dev);
   cudaFree(c->anom_dev);
+  cudaFree(c->hist_own);
   cudaFree(c->params_out_dev);
   cudaFree(c->props_out_dev);
   cudaFree(c->counters_dev_out);
@@ -283,10 +311,99 @@ int fmc_set_data(fmc_context* c, int model, int ndata, const double* x, const do
   FMC_CUDA(cudaMemcpyAsync(c->rows_dev, c->rows_host.data(), sizeof(RowData) * n_pad, cudaMemcpyHostToDevice,
                            c->stream));
   FMC_CUDA(cudaStreamSynchronize(c->stream));
+  if (model != c->model) c->hist_bins = 0;  // the binned quantities belong to a model
   c->model = model;
   c->n = ndata;
   c->n_pad = n_pad;
   return FMC_OK;
+}
+
+int fmc_set_histogram(fmc_context* c, int nbins, const double* lo, const double* hi) {
+  if (!c || nbins < 0 || nbins > (1 << 24)) return FMC_ERR_BAD_ARG;
+  if (nbins == 0) {
+    c->hist_bins = 0;
+    return FMC_OK;
+  }
+  if (c->model < 0) return FMC_ERR_NO_DATA;
+  if (!lo || !hi) return FMC_ERR_BAD_ARG;
+  const ModelEntry& m = models()[c->model];
+  const int nq = m.nparam + m.nprop;
+  if (nq > fmc::HIST_MAX_QUANT) return FMC_ERR_BAD_ARG;
+  for (int j = 0; j < nq; ++j)
+    if (!(hi[j] > lo[j]) || !std::isfinite(lo[j]) || !std::isfinite(hi[j])) return FMC_ERR_BAD_ARG;
+  FMC_CUDA(cudaSetDevice(c->device));
+  if (c->inflight >= 0) FMC_CUDA(cudaStreamSynchronize(c->stream));
+  const long long need = (long long)nq * (nbins + 2);
+  if (need > c->hist_own_cap) {
+    const bool was_own = c->hist == c->hist_own;
+    cudaFree(c->hist_own);
+    c->hist_own = nullptr;
+    c->hist_own_cap = 0;
+    FMC_CUDA(cudaMalloc(&c->hist_own, sizeof(unsigned long long) * need));
+    c->hist_own_cap = need;
+    if (was_own) c->hist = c->hist_own;
+  }
+  if (!c->hist) c->hist = c->hist_own;
+  for (int j = 0; j < nq; ++j) {
+    c->hist_lo[j] = lo[j];
+    c->hist_scale[j] = (double)nbins / (hi[j] - lo[j]);
+  }
+  c->hist_bins = nbins;
+  return FMC_OK;
+}
+
+long long fmc_histogram_len(const fmc_context* c) {
+  if (!c || c->model < 0 || c->hist_bins <= 0) return 0;
+  const ModelEntry& m = models()[c->model];
+  return (long long)(m.nparam + m.nprop) * (c->hist_bins + 2);
+}
+
+int fmc_set_histogram_dev(fmc_context* c, unsigned long long* counts_dev) {
+  if (!c) return FMC_ERR_BAD_ARG;
+  c->hist = counts_dev ? counts_dev : c->hist_own;
+  return FMC_OK;
+}
+
+int fmc_get_histogram(fmc_context* c, unsigned long long* counts_host) {
+  if (!c || !counts_host) return FMC_ERR_BAD_ARG;
+  const long long len = fmc_histogram_len(c);
+  if (len <= 0 || !c->hist) return FMC_ERR_STATE;
+  FMC_CUDA(cudaSetDevice(c->device));
+  FMC_CUDA(cudaMemcpyAsync(counts_host, c->hist, sizeof(unsigned long long) * len, cudaMemcpyDeviceToHost,
+                           c->stream));
+  FMC_CUDA(cudaStreamSynchronize(c->stream));
+  return FMC_OK;
+}
+
+long long fmc_histogram_quantiles(const unsigned long long* counts, int nbins, double lo, double hi,
+                                  const double* probs, int nprobs, double* out) {
+  if (!counts || nbins <= 0 || !(hi > lo) || nprobs < 0 || (nprobs > 0 && (!probs || !out))) return -1;
+  unsigned long long total = 0;
+  for (int b = 0; b < nbins + 2; ++b) total += counts[b];
+  const double width = (hi - lo) / (double)nbins;
+  for (int i = 0; i < nprobs; ++i) {
+    if (total == 0 || !(probs[i] >= 0.0) || !(probs[i] <= 1.0)) {
+      out[i] = std::nan("");
+      continue;
+    }
+    const double target = probs[i] * (double)total;  // resamples below the quantile
+    double below = (double)counts[0];
+    if (target <= below && counts[0] > 0) {
+      out[i] = lo;
+      continue;
+    }
+    double q = hi;
+    for (int b = 1; b <= nbins; ++b) {
+      const double in_bin = (double)counts[b];
+      if (in_bin > 0.0 && target <= below + in_bin) {
+        q = lo + width * ((double)(b - 1) + (target - below) / in_bin);
+        break;
+      }
+      below += in_bin;
+    }
+    out[i] = q;
+  }
+  return (long long)(counts[0] + counts[nbins + 1]);
 }
 
 int fmc_accumulator_len(const fmc_context* c) {
@@ -310,9 +427,16 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   if (c->inflight >= 0) FMC_CUDA(cudaStreamSynchronize(c->stream));
   const int P = m.nparam, Q = m.nprop;
   c->keep = keep_per_resample != 0;
-  if (c->keep) {
-    const long long need_p = (long long)P * nresample, need_q = (long long)(Q > 0 ? Q : 1) * nresample,
-                    need_c = 10LL * nresample;
+  // chunking: the pipeline keeps ~0.4 KB of state per fit between its kernels
+  const long long kChunk = 1LL << 21;
+  const long long cap = nresample < kChunk ? (nresample > 0 ? nresample : 1) : kChunk;
+  const bool binning = c->hist_bins > 0 && c->hist != nullptr;
+  if (c->keep || binning) {
+    // per-resample results: the whole run when the caller keeps them, else one chunk of scratch
+    // for the binning kernel
+    const long long rows_out = c->keep ? nresample : cap;
+    const long long need_p = (long long)P * rows_out, need_q = (long long)(Q > 0 ? Q : 1) * rows_out,
+                    need_c = c->keep ? 10LL * nresample : 0;
     if (need_p > c->out_cap_p) {
       cudaFree(c->params_out_dev);
       c->params_out_dev = nullptr;
@@ -335,9 +459,6 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
       c->out_cap_c = need_c;
     }
   }
-  // chunking: the pipeline keeps ~0.4 KB of state per fit between its kernels
-  const long long kChunk = 1LL << 21;
-  const long long cap = nresample < kChunk ? (nresample > 0 ? nresample : 1) : kChunk;
   const int PP = P * (P + 1) / 2;
   if (cap > c->chunk_cap || P != c->chunk_p) {
     cudaFree(c->xbuf);
@@ -380,6 +501,18 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   a.cnt = c->cnt;
   a.acc = c->acc;
   a.anom = c->anom_dev;
+  fmc::HistArgs h;
+  std::memset(&h, 0, sizeof(h));
+  if (binning) {
+    h.hist = c->hist;
+    h.bins = c->hist_bins;
+    h.np = P;
+    h.nq = Q;
+    for (int j = 0; j < P + Q; ++j) {
+      h.lo[j] = c->hist_lo[j];
+      h.scale[j] = c->hist_scale[j];
+    }
+  }
 
   // data in shared memory when it fits (227 KB opt-in on B200), else through L1/L2
   size_t shmem = sizeof(RowData) * (size_t)c->n_pad;
@@ -417,6 +550,8 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 2 * nchunks, c->stream));
   FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
   FMC_CUDA(cudaMemsetAsync(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP), c->stream));
+  if (binning)
+    FMC_CUDA(cudaMemsetAsync(h.hist, 0, sizeof(unsigned long long) * (size_t)(P + Q) * (h.bins + 2), c->stream));
   FMC_CUDA(cudaEventRecord(c->ev0, c->stream));
   if (shared_init && nresample > 0) FMC_CUDA(m.launch_jac0(a, c->rowj_dev, g0_dev, c->stream));
   for (long long ch = 0; ch < nchunks; ++ch) {
@@ -424,8 +559,9 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     a.first = first_counter + lo;
     a.nres = cnt;
     a.z_inject = inject ? z_inject_dev + (size_t)lo * c->n : nullptr;
-    a.params_out = c->keep ? c->params_out_dev + (size_t)lo * P : nullptr;
-    a.props_out = c->keep ? c->props_out_dev + (size_t)lo * (Q > 0 ? Q : 1) : nullptr;
+    const size_t out_row = c->keep ? (size_t)lo : 0;  // scratch is reused by every chunk
+    a.params_out = (c->keep || binning) ? c->params_out_dev + out_row * P : nullptr;
+    a.props_out = (c->keep || binning) ? c->props_out_dev + out_row * (Q > 0 ? Q : 1) : nullptr;
     a.counters_out = c->keep ? c->counters_dev_out + (size_t)lo * 10 : nullptr;
     long long grid = full_grid;
     const long long need = (cnt + FMC_THREADS - 1) / FMC_THREADS;
@@ -440,6 +576,18 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
       else
         FMC_CUDA(m.launch_init(a, inject, smem, shmem, c->stream));
       FMC_CUDA(m.launch_iter(a, inject, smem, (int)grid, shmem, c->stream));
+    }
+    if (binning) {
+      h.params = a.params_out;
+      h.props = a.props_out;
+      h.nres = cnt;
+      const long long work = cnt * (P + Q);
+      long long hgrid = (work + 255) / 256;
+      const long long hmax = (long long)c->num_sms * 8;
+      if (hgrid > hmax) hgrid = hmax;
+      if (hgrid < 1) hgrid = 1;
+      hist_kernel<<<(unsigned)hgrid, 256, 0, c->stream>>>(h);
+      FMC_CUDA(cudaGetLastError());
     }
   }
   FMC_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -567,11 +715,13 @@ int cached_context(int device, fmc_context** out) {
 }
 }  // namespace
 
-int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, const double* err_y,
-                      const double* params_start, long long nresample, unsigned long long seed,
-                      long long first_counter, int ngpus, const double* z_inject, double* sum_p,
-                      double* sum_p2, double* sum_prop, double* sum_prop2, double* params_out,
-                      double* props_out, long long* rc_count, long long* totals) {
+namespace {
+int bootstrap_run_impl(int model, int ndata, const double* x, const double* y, const double* err_y,
+                       const double* params_start, long long nresample, unsigned long long seed,
+                       long long first_counter, int ngpus, const double* z_inject, double* sum_p,
+                       double* sum_p2, double* sum_prop, double* sum_prop2, double* params_out,
+                       double* props_out, long long* rc_count, long long* totals, int nbins, const double* bin_lo,
+                       const double* bin_hi, unsigned long long* counts) {
   if (model < 0 || model >= fmc_model_count()) return FMC_ERR_BAD_MODEL;
   if (!x || !y || !err_y || !params_start || nresample < 0 || ngpus < 0) return FMC_ERR_BAD_ARG;
   const int ndev = device_count();
@@ -585,6 +735,8 @@ int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, co
   std::vector<int> rcs(G, FMC_OK);
   std::vector<std::string> errs(G);
   std::vector<std::vector<double>> accs(G, std::vector<double>(AL, 0.0));
+  const size_t HL = nbins > 0 ? (size_t)(P + Q) * (nbins + 2) : 0;
+  std::vector<std::vector<unsigned long long>> hists(G, std::vector<unsigned long long>(HL, 0ULL));
   auto shard = [&](int g) {
     // contiguous split of the resample ids
     const long long lo = nresample * g / G, hi = nresample * (g + 1) / G, cnt = hi - lo;
@@ -606,12 +758,17 @@ int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, co
         }
       }
       fmc_set_accumulator_dev(c, nullptr);
+      fmc_set_histogram_dev(c, nullptr);
+      if ((rc = fmc_set_histogram(c, nbins, bin_lo, bin_hi)) != FMC_OK) break;  // cached context: also switches off
       if ((rc = fmc_launch(c, params_start, cnt, seed, first_counter + lo, zdev, keep ? 1 : 0)) != FMC_OK) break;
       rc = fmc_finish(c, nullptr, nullptr, nullptr, nullptr, params_out ? params_out + (size_t)lo * P : nullptr,
                       (props_out && Q > 0) ? props_out + (size_t)lo * Q : nullptr, nullptr, nullptr, nullptr);
       if (rc != FMC_OK) break;
-      if (cudaMemcpy(accs[g].data(), c->acc, sizeof(double) * AL, cudaMemcpyDeviceToHost) != cudaSuccess)
+      if (cudaMemcpy(accs[g].data(), c->acc, sizeof(double) * AL, cudaMemcpyDeviceToHost) != cudaSuccess) {
         rc = FMC_ERR_CUDA;
+        break;
+      }
+      if (HL > 0) rc = fmc_get_histogram(c, hists[g].data());
     } while (0);
     if (zdev) cudaFree(zdev);
     rcs[g] = rc;
@@ -633,8 +790,35 @@ int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, co
   std::vector<double> acc(AL, 0.0);
   for (int g = 0; g < G; ++g)
     for (int i = 0; i < AL; ++i) acc[i] += accs[g][i];
+  if (HL > 0 && counts) {
+    for (size_t i = 0; i < HL; ++i) counts[i] = 0ULL;
+    for (int g = 0; g < G; ++g)
+      for (size_t i = 0; i < HL; ++i) counts[i] += hists[g][i];
+  }
   return fmc_decode_accumulator(model, params_start, acc.data(), sum_p, sum_p2, sum_prop, sum_prop2, nullptr,
                                 rc_count, totals);
+}
+}  // namespace
+
+int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, const double* err_y,
+                      const double* params_start, long long nresample, unsigned long long seed,
+                      long long first_counter, int ngpus, const double* z_inject, double* sum_p,
+                      double* sum_p2, double* sum_prop, double* sum_prop2, double* params_out,
+                      double* props_out, long long* rc_count, long long* totals) {
+  return bootstrap_run_impl(model, ndata, x, y, err_y, params_start, nresample, seed, first_counter, ngpus, z_inject,
+                            sum_p, sum_p2, sum_prop, sum_prop2, params_out, props_out, rc_count, totals, 0, nullptr,
+                            nullptr, nullptr);
+}
+
+int fmc_bootstrap_run_binned(int model, int ndata, const double* x, const double* y, const double* err_y,
+                             const double* params_start, long long nresample, unsigned long long seed,
+                             long long first_counter, int ngpus, double* sum_p, double* sum_p2, double* sum_prop,
+                             double* sum_prop2, long long* rc_count, long long* totals, int nbins,
+                             const double* bin_lo, const double* bin_hi, unsigned long long* counts) {
+  if (nbins <= 0 || !bin_lo || !bin_hi || !counts) return FMC_ERR_BAD_ARG;
+  return bootstrap_run_impl(model, ndata, x, y, err_y, params_start, nresample, seed, first_counter, ngpus, nullptr,
+                            sum_p, sum_p2, sum_prop, sum_prop2, nullptr, nullptr, rc_count, totals, nbins, bin_lo,
+                            bin_hi, counts);
 }
 
 int fmc_fit_once(int model, int ndata, const double* x, const double* y, const double* err_y, double* params,

@@ -54,3 +54,32 @@ def allreduce_accumulator(acc):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
     return acc
+
+
+def bin_values(values, nbins, lo, hi):
+    """Host image of the device binning (fmc::hist_bin, bootstrap_kernel.cuh): counts
+    [ncol][nbins + 2] of `values` [nfit][ncol]; column 0 = underflow and NaN, nbins + 1 = overflow.
+    The same three FP64 operations as the kernel, so the counts agree exactly."""
+    v = np.asarray(values, dtype=np.float64)
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    scale = float(nbins) / (hi - lo)
+    out = np.zeros((v.shape[1], nbins + 2), dtype=np.uint64)
+    for j in range(v.shape[1]):
+        t = (v[:, j] - lo[j]) * scale[j]
+        b = np.zeros(len(t), dtype=np.int64)
+        inside = (t >= 0.0) & (t < float(nbins))
+        b[inside] = 1 + t[inside].astype(np.int64)
+        b[t >= float(nbins)] = nbins + 1
+        out[j] = np.bincount(b, minlength=nbins + 2).astype(np.uint64)
+    return out
+
+
+def allreduce_histogram(counts):
+    """Sum the binned distributions over ranks.  `counts` is a torch int64 tensor (the device
+    buffer handed to fmc_set_histogram_dev, or a CPU tensor with gloo).  Integer sums: the
+    result is exact and independent of the rank order."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts

@@ -39,6 +39,35 @@ MODULE fmc_b200_bindings
       INTEGER(c_int) :: rc
     END FUNCTION fmc_bootstrap_run
 
+    ! The same loop with make_histogram=.TRUE. for large nrand_points: instead of one
+    ! WRITE(8+j,*)props(j) per resample (bootstrap.f90:319-325) every parameter and property is
+    ! binned on the GPU; counts is INTEGER(c_long_long) (nbins+2, nparam+nprop), first and last
+    ! row of a column = resamples below bin_lo / at or above bin_hi.
+    FUNCTION fmc_bootstrap_run_binned(model, ndata, x, y, err_y, params_start, nresample, seed, &
+      &first_counter, ngpus, sum_p, sum_p2, sum_prop, sum_prop2, rc_count, totals, nbins, &
+      &bin_lo, bin_hi, counts) BIND(C, name='fmc_bootstrap_run_binned') RESULT(rc)
+      IMPORT :: c_int, c_double, c_long_long, c_ptr
+      INTEGER(c_int), VALUE :: model, ndata, ngpus, nbins
+      REAL(c_double), INTENT(in) :: x(*), y(*), err_y(*), params_start(*), bin_lo(*), bin_hi(*)
+      INTEGER(c_long_long), VALUE :: nresample, seed, first_counter
+      REAL(c_double), INTENT(out) :: sum_p(*), sum_p2(*), sum_prop(*), sum_prop2(*)
+      TYPE(c_ptr), VALUE :: rc_count, totals
+      INTEGER(c_long_long), INTENT(out) :: counts(*)
+      INTEGER(c_int) :: rc
+    END FUNCTION fmc_bootstrap_run_binned
+
+    ! Quantiles of one quantity from its column of counts.
+    FUNCTION fmc_histogram_quantiles(counts, nbins, lo, hi, probs, nprobs, out) &
+      &BIND(C, name='fmc_histogram_quantiles') RESULT(outside)
+      IMPORT :: c_int, c_double, c_long_long
+      INTEGER(c_long_long), INTENT(in) :: counts(*)
+      INTEGER(c_int), VALUE :: nbins, nprobs
+      REAL(c_double), VALUE :: lo, hi
+      REAL(c_double), INTENT(in) :: probs(*)
+      REAL(c_double), INTENT(out) :: out(*)
+      INTEGER(c_long_long) :: outside
+    END FUNCTION fmc_histogram_quantiles
+
     ! offset_data(.FALSE.) ; fit_data(params)  -- bootstrap.f90:288-291
     FUNCTION fmc_fit_once(model, ndata, x, y, err_y, params, rc2) &
       &BIND(C, name='fmc_fit_once') RESULT(rc)

@@ -6,7 +6,9 @@
 //
 // Environment (extensions; defaults reproduce the reference): FMC_NRAND (nrand_points, default
 // 100000, bootstrap.f90:9), FMC_SEED (31415, utils.f90:7), FMC_NGPUS (1), FMC_MODEL (0),
-// FMC_HISTOGRAM (1 = write histogram_<prop>.dat, bootstrap.f90:263).
+// FMC_HISTOGRAM (1 = write histogram_<prop>.dat, bootstrap.f90:263), FMC_HISTOGRAM_BINS (> 0:
+// bin the properties on the GPU instead of dumping one text line per resample -- the form that
+// scales to 1e8 resamples; histogram_<prop>.dat then holds "bin centre, count" lines).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -148,12 +150,64 @@ int main(int argc, char** argv) {
   const bool make_histogram = !(std::getenv("FMC_HISTOGRAM") && std::atoi(std::getenv("FMC_HISTOGRAM")) == 0);
   std::vector<double> sp(m.nparam), sp2(m.nparam), sq(props.size()), sq2(props.size());
   std::vector<double> props_all;
-  if (make_histogram && m.nprop > 0) props_all.resize((size_t)nrand * m.nprop);
-  rc = fmc_bootstrap_run(m.id, ndata, d.x.data(), d.y.data(), d.err.data(), params.data(), nrand, seed, 0, ngpus,
-                         nullptr, sp.data(), sp2.data(), sq.data(), sq2.data(), nullptr,
-                         props_all.empty() ? nullptr : props_all.data(), nullptr, nullptr);
+  const int nbins = std::getenv("FMC_HISTOGRAM_BINS") ? std::atoi(std::getenv("FMC_HISTOGRAM_BINS")) : 0;
+  const bool binned = make_histogram && nbins > 0 && m.nprop > 0;
+  const int nquant = m.nparam + m.nprop;
+  std::vector<double> blo(nquant), bhi(nquant);
+  std::vector<unsigned long long> counts;
+  if (binned) {
+    // range of every quantity from a pilot of a few thousand resamples (ids from the far end of
+    // the id space, so the run proper does not repeat them): mean -/+ 8 standard deviations
+    const long long npilot = 4096;
+    std::vector<double> pp((size_t)npilot * m.nparam), pq((size_t)npilot * m.nprop);
+    rc = fmc_bootstrap_run(m.id, ndata, d.x.data(), d.y.data(), d.err.data(), params.data(), npilot, seed,
+                           (1LL << 62) - npilot, 1, nullptr, sp.data(), sp2.data(), sq.data(), sq2.data(), pp.data(),
+                           pq.data(), nullptr, nullptr);
+    if (rc != FMC_OK) errstop("MONTE_CARLO_FIT_DATA", std::string(fmc_strerror(rc)) + " " + fmc_last_cuda_error());
+    for (int j = 0; j < nquant; ++j) {
+      const double* v = j < m.nparam ? pp.data() + j : pq.data() + (j - m.nparam);
+      const int stride = j < m.nparam ? m.nparam : m.nprop;
+      double mean = 0.0, var = 0.0;
+      long long cnt = 0;
+      for (long long i = 0; i < npilot; ++i)
+        if (std::isfinite(v[i * stride])) {
+          mean += v[i * stride];
+          ++cnt;
+        }
+      mean /= (double)(cnt > 0 ? cnt : 1);
+      for (long long i = 0; i < npilot; ++i)
+        if (std::isfinite(v[i * stride])) var += (v[i * stride] - mean) * (v[i * stride] - mean);
+      double sd = std::sqrt(var / (double)(cnt > 1 ? cnt - 1 : 1));
+      if (!(sd > 0.0)) sd = 0.0625;
+      blo[j] = mean - 8.0 * sd;
+      bhi[j] = mean + 8.0 * sd;
+    }
+    counts.resize((size_t)nquant * (nbins + 2));
+    rc = fmc_bootstrap_run_binned(m.id, ndata, d.x.data(), d.y.data(), d.err.data(), params.data(), nrand, seed, 0,
+                                  ngpus, sp.data(), sp2.data(), sq.data(), sq2.data(), nullptr, nullptr, nbins,
+                                  blo.data(), bhi.data(), counts.data());
+  } else {
+    if (make_histogram && m.nprop > 0) props_all.resize((size_t)nrand * m.nprop);
+    rc = fmc_bootstrap_run(m.id, ndata, d.x.data(), d.y.data(), d.err.data(), params.data(), nrand, seed, 0, ngpus,
+                           nullptr, sp.data(), sp2.data(), sq.data(), sq2.data(), nullptr,
+                           props_all.empty() ? nullptr : props_all.data(), nullptr, nullptr);
+  }
   if (rc != FMC_OK) errstop("MONTE_CARLO_FIT_DATA", std::string(fmc_strerror(rc)) + " " + fmc_last_cuda_error());
-  if (make_histogram) {
+  if (binned) {
+    for (int j = 0; j < m.nprop; ++j) {
+      const std::string fn = "histogram_" + trim(m.qname[j]) + ".dat";
+      FILE* f = std::fopen(fn.c_str(), "w");
+      if (!f) errstop("MONTE_CARLO_FIT_DATA", "Error opening " + fn + ".");
+      const int q = m.nparam + j;
+      const unsigned long long* c = counts.data() + (size_t)q * (nbins + 2);
+      const double width = (bhi[q] - blo[q]) / (double)nbins;
+      std::fprintf(f, "# binned on the GPU: %d bins on [%.17g, %.17g); below: %llu; above: %llu\n", nbins, blo[q],
+                   bhi[q], c[0], c[nbins + 1]);
+      for (int b = 1; b <= nbins; ++b)
+        std::fprintf(f, "%s %llu\n", list_directed_real(blo[q] + width * ((double)b - 0.5)).c_str(), c[b]);
+      std::fclose(f);
+    }
+  } else if (make_histogram) {
     for (int j = 0; j < m.nprop; ++j) {
       const std::string fn = "histogram_" + trim(m.qname[j]) + ".dat";
       FILE* f = std::fopen(fn.c_str(), "w");
@@ -173,6 +227,18 @@ int main(int argc, char** argv) {
   if (make_histogram) {
     for (int j = 0; j < m.nprop; ++j)
       std::printf("   Histogram of %s written to histogram_%s.dat.\n", trim(m.qname[j]).c_str(), trim(m.qname[j]).c_str());
+    std::printf("\n");
+  }
+  if (binned) {  // extension: central 68% / 95% intervals straight from the binned distributions
+    const double probs[5] = {0.025, 0.16, 0.5, 0.84, 0.975};
+    for (int j = 0; j < m.nprop; ++j) {
+      const int q = m.nparam + j;
+      double qs[5];
+      fmc_histogram_quantiles(counts.data() + (size_t)q * (nbins + 2), nbins, blo[q], bhi[q], probs, 5, qs);
+      std::printf("   Quantiles of %s (2.5, 16, 50, 84, 97.5 %%):\n  ", m.qname[j]);
+      for (int k = 0; k < 5; ++k) std::printf(" %.10g", qs[k]);
+      std::printf("\n");
+    }
     std::printf("\n");
   }
   std::printf(" Program finished.\n\n");

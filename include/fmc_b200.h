@@ -128,6 +128,45 @@ int fmc_decode_accumulator(int model, const double* params_start, const double* 
  * run) and fills up to `cap` global resample ids and flag words (bit0 lmstep, bit1 gqtstp, bit2
  * step recomputation, bit3 passes; bits 8+ = which nl2sno call).  Call after fmc_finish/fmc_wait. */
 int fmc_last_anomalies(fmc_context* ctx, long long* ids, int* flags, int cap);
+
+/* ---- binned distributions -------------------------------------------
+ * Replaces the reference's histogram_<prop>.dat dumps -- one list-directed text line per
+ * resample and property, written inside an OMP CRITICAL (bootstrap.f90:301-308, 319-325,
+ * 348-355) -- which cannot scale to 1e8 resamples.  The fit kernel bins every fitted
+ * parameter and derived property as the fit finishes; the counts are 64-bit integers, so the
+ * result is exact and independent of the order in which fits finish or GPUs are combined.
+ *
+ * Quantity j (j < nparam: parameter j, else property j - nparam) has `nbins` equal-width bins
+ * on [lo[j], hi[j]); counts are laid out [nparam + nprop][nbins + 2] with column 0 =
+ * underflow (and NaN), 1..nbins the bins, nbins + 1 = overflow; bin(v) =
+ * 1 + (int)((v - lo) * (nbins / (hi - lo))).  nbins = 0 switches binning off.  Needs
+ * fmc_set_data first (the model fixes the number of quantities); the counts are zeroed at the
+ * start of every fmc_launch, like the accumulator. */
+int fmc_set_histogram(fmc_context* ctx, int nbins, const double* lo, const double* hi);
+/* Number of 64-bit counts, (nparam + nprop) * (nbins + 2); 0 when binning is off. */
+long long fmc_histogram_len(const fmc_context* ctx);
+/* Let the counts live in caller-owned DEVICE memory (fmc_histogram_len() uint64), e.g. a
+ * torch int64 tensor that is all-reduced across ranks afterwards.  NULL = internal buffer. */
+int fmc_set_histogram_dev(fmc_context* ctx, unsigned long long* counts_dev);
+/* Wait for the launch and copy the counts of this GPU to the host. */
+int fmc_get_histogram(fmc_context* ctx, unsigned long long* counts_host);
+/* Quantiles of ONE quantity from its nbins + 2 counts: the value below which a fraction
+ * probs[i] of the binned resamples lies, linear within a bin.  A quantile that falls in the
+ * underflow / overflow column is reported as lo / hi.  Returns the number of resamples that
+ * fell outside [lo, hi) -- widen the range if that is not negligible -- or < 0 on bad input. */
+long long fmc_histogram_quantiles(const unsigned long long* counts, int nbins, double lo, double hi,
+                                  const double* probs, int nprobs, double* out);
+
+/* One-call form: fmc_bootstrap_run without per-resample arrays but with the binned
+ * distributions of all nparam + nprop quantities, summed over the GPUs used.  This is what a
+ * make_histogram=.TRUE. run of the reference (bootstrap.f90:301-325) binds for large N. */
+int fmc_bootstrap_run_binned(int model, int ndata, const double* x, const double* y,
+                             const double* err_y, const double* params_start, long long nresample,
+                             unsigned long long seed, long long first_counter, int ngpus,
+                             double* sum_p, double* sum_p2, double* sum_prop, double* sum_prop2,
+                             long long* rc_count, long long* totals, int nbins,
+                             const double* bin_lo, const double* bin_hi, unsigned long long* counts);
+
 /* Device time of the last fit kernel (CUDA events on the launching stream), milliseconds. */
 float fmc_last_kernel_ms(fmc_context* ctx);
 /* Grid geometry chosen for the last launch: blocks, threads per block, blocks per SM, SMs. */

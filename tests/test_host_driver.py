@@ -136,3 +136,32 @@ def test_fitter_mc_transcript_on_the_probe_file(tmp_path, oracle):
     assert re.search(r"=\s+0\.50\(1\)", t) and re.search(r"Property  ab =", t)
     h = np.loadtxt(tmp_path / "histogram_ab.dat")
     assert h.shape == (100000,) and abs(h.mean() - 2.4650) < 0.001
+
+
+@pytest.mark.gpu
+def test_fitter_mc_binned_histogram_mode(tmp_path):
+    """FMC_HISTOGRAM_BINS: histogram_<prop>.dat holds bin centres and counts from the device-side
+    binning (row f4) instead of one line per resample; same transcript, same moments."""
+    subprocess.check_call(["make", "-C", PKG, "fitter_mc"], stdout=subprocess.DEVNULL)
+    x, y, err = datasets.c1_probe()
+    np.savetxt(tmp_path / "probe.dat", np.c_[x, y, err])
+    env = dict(os.environ, FMC_HISTOGRAM_BINS="400", FMC_NRAND="200000")
+    out = subprocess.run([os.path.join(PKG, "fitter_mc"), "probe.dat"], cwd=tmp_path, capture_output=True, text=True,
+                         timeout=120, env=env)
+    assert out.returncode == 0, out.stderr
+    t = out.stdout
+    assert " Monte Carlo fitted parameter set (using 200000 random points):" in t
+    assert "   Histogram of ab written to histogram_ab.dat." in t
+    head = open(tmp_path / "histogram_ab.dat").readline()
+    assert head.startswith("# binned on the GPU: 400 bins on [")
+    below, above = (int(v) for v in re.search(r"below: (\d+); above: (\d+)", head).groups())
+    h = np.loadtxt(tmp_path / "histogram_ab.dat")
+    assert h.shape == (400, 2) and int(h[:, 1].sum()) + below + above == 200000
+    assert below + above < 20                                   # +/- 8 sigma
+    mean = (h[:, 0] * h[:, 1]).sum() / h[:, 1].sum()
+    mc = re.findall(r"Property  ab =\s+([-0-9.E+]+)\s+\+/-\s+([-0-9.E+]+)", t)
+    assert abs(mean - float(mc[0][0])) < 2e-4                    # binned mean vs the exact moment sums
+    qs = [float(v) for v in re.search(r"Quantiles of ab.*\n\s+(.*)\n", t).group(1).split()]
+    assert len(qs) == 5 and np.all(np.diff(qs) > 0)
+    sd = float(mc[0][1])
+    assert abs((qs[3] - qs[1]) / 2 - sd) < 0.05 * sd and abs(qs[2] - float(mc[0][0])) < 0.05 * sd
