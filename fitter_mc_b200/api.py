@@ -78,6 +78,8 @@ def lib():
     L.fmc_bootstrap_run_binned.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, C.c_ulonglong,
                                            C.c_longlong, C.c_int, _dp, _dp, _dp, _dp, _lp, _lp, C.c_int, _dp, _dp,
                                            C.c_void_p]
+    L.fmc_set_jacobian_mode.argtypes = [C.c_void_p, C.c_int]
+    L.fmc_model_has_analytic_jacobian.argtypes = [C.c_int]
     L.fmc_set_histogram.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     L.fmc_histogram_len.restype = C.c_longlong
     L.fmc_histogram_len.argtypes = [C.c_void_p]
@@ -331,6 +333,12 @@ class Context:
 
     def wait(self):
         _check(lib().fmc_wait(self._h), "fmc_wait")
+
+    def set_jacobian_mode(self, mode):
+        """"forward-difference" (nl2sno, the reference's path; default) or "analytic" (nl2sol + madj,
+        README:35-42): exact Jacobian rows from the plug-in's model_grad or by dual numbers."""
+        code = {"forward-difference": 0, "fd": 0, 0: 0, "analytic": 1, 1: 1}[mode]
+        _check(lib().fmc_set_jacobian_mode(self._h, code), "fmc_set_jacobian_mode")
 
     def set_histogram(self, nbins, lo=None, hi=None):
         """Bin every fitted parameter and property on the device (replaces histogram_<prop>.dat,

@@ -109,7 +109,7 @@ FMC_INLINE __device__ void kahan_add(double& s, double& c, double v) {
 }
 
 // One streaming pass of one fit over the n data points.
-template <class M, bool INJECT, bool WITH_B>
+template <class M, bool INJECT, bool WITH_B, int JAC = JAC_FD>
 FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, int n_pad,
                                      unsigned long long seed, unsigned long long id,
                                      const double* __restrict__ zrow,
@@ -128,7 +128,7 @@ FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, in
       else
         zz = (double)z[m];
       const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
-      row_accumulate<M, WITH_B>(pa, pb, rd.x, yfit, rd.rerr, acc);
+      row_accumulate<M, WITH_B, JAC>(pa, pb, rd.x, yfit, rd.rerr, acc);
     }
   }
 }
@@ -149,7 +149,7 @@ FMC_INLINE __device__ const RowData* stage_rows(const KernelArgs& a, unsigned ch
 // toms573.f90:695-733 with D = 1).  Every fit does exactly the same amount of work here and
 // none needs the J(x0)^T r(x) part, so this stage runs as its own, perfectly uniform kernel:
 // one fit per thread, static assignment, no solver code.
-template <class M, bool INJECT, bool SMEM>
+template <class M, bool INJECT, bool SMEM, int JAC = JAC_FD>
 __global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int PP = P * (P + 1) / 2;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     x[i] = a.call == 0 ? a.start[i] : a.xbuf[i * a.cap + slot];
-    h[i] = k::dltfdj * fmax(fabs(x[i]), 1.0);  // toms573.f90:716 with D = 1
+    h[i] = JAC == JAC_ANALYTIC ? 1.0 : k::dltfdj * fmax(fabs(x[i]), 1.0);  // toms573.f90:716 with D = 1
   }
   PassPoint<P> pa;
   pa.set(x, h);
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs
   acc.zero();
   const unsigned long long id = (unsigned long long)(a.first + slot);
   const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
-  pass_loop<M, INJECT, false>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pa, acc);
+  pass_loop<M, INJECT, false, JAC>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pa, acc);
   double f, g[P], G[PP], lky[P];
   pass_scale<P>(acc, h, h, f, g, G, lky);
   a.init[slot] = f;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(FMC_THREADS) init_shared_kernel(const KernelAr
 // that finishes takes the next fit from a shared counter, so lanes of a warp are at different
 // iterations of different fits but always execute the same thing next -- one trial pass
 // (residual + speculative Jacobian at x, Jacobian at x0 for the secant update).
-template <class M, bool INJECT, bool SMEM>
+template <class M, bool INJECT, bool SMEM, int JAC = JAC_FD>
 __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int Q = M::NPROP;
@@ -406,14 +406,17 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
   while (__any_sync(0xffffffffu, active)) {
     if (active) {
       PassPoint<P> pa, pb;
-      pa.set(s.x, s.hA);
+      pa.set(s.x, s.hA);   // (the steps are not used by an analytic pass)
       pb.set(s.x0, s.hJ);
       PassAcc<P> acc;
       acc.zero();
       const unsigned long long id = (unsigned long long)(a.first + slot);
       const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
-      pass_loop<M, INJECT, true>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
-      pass_finish<P>(acc, s);
+      pass_loop<M, INJECT, true, JAC>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
+      if constexpr (JAC == JAC_ANALYTIC)
+        pass_finish_analytic<P>(acc, s);
+      else
+        pass_finish<P>(acc, s);
       ++fit_passes;
       bool more = s.resume();
       if (more && fit_passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call

@@ -29,6 +29,7 @@ using fmc::RowData;
 namespace {
 
 thread_local std::string g_last_cuda_error;
+int g_default_jac = 0;  // Jacobian mode of the one-call entry points (fmc_set_jacobian_mode(NULL, .))
 
 #define FMC_CUDA(call)                                                                   \
   do {                                                                                   \
@@ -143,6 +144,7 @@ struct fmc_context {
   unsigned long long* hist = nullptr;
   long long hist_own_cap = 0;
   int hist_bins = 0;
+  int jac = fmc::JAC_FD;  // how Jacobian rows are formed (fmc_set_jacobian_mode)
   double hist_lo[fmc::HIST_MAX_QUANT] = {0};
   double hist_scale[fmc::HIST_MAX_QUANT] = {0};
   long long rowj_cap = 0;
@@ -316,6 +318,20 @@ int fmc_set_data(fmc_context* c, int model, int ndata, const double* x, const do
   c->n = ndata;
   c->n_pad = n_pad;
   return FMC_OK;
+}
+
+int fmc_set_jacobian_mode(fmc_context* c, int mode) {
+  if (mode != FMC_JACOBIAN_FORWARD_DIFFERENCE && mode != FMC_JACOBIAN_ANALYTIC) return FMC_ERR_BAD_ARG;
+  if (c)
+    c->jac = mode;
+  else
+    g_default_jac = mode;  // the one-call entry points
+  return FMC_OK;
+}
+
+int fmc_model_has_analytic_jacobian(int model) {
+  if (model < 0 || model >= fmc_model_count()) return 0;
+  return models()[model].analytic ? 1 : 0;
 }
 
 int fmc_set_histogram(fmc_context* c, int nbins, const double* lo, const double* hi) {
@@ -520,7 +536,9 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   if (!smem) shmem = 0;
   const bool inject = z_inject_dev != nullptr;
   int bps = 0;
-  FMC_CUDA(m.occupancy(inject, smem, shmem, &bps));
+  const int jac = c->jac;
+  if (jac == fmc::JAC_ANALYTIC && !m.analytic) return FMC_ERR_BAD_ARG;  // double-only model_y, no model_grad
+  FMC_CUDA(m.occupancy(inject, smem, jac, shmem, &bps));
   if (bps < 1) {
     g_last_cuda_error = "kernel does not fit on an SM";
     return FMC_ERR_CUDA;
@@ -533,7 +551,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
 
   // first nl2sno call: shared Jacobian at params_start when its rows fit in shared memory too
   const size_t shmem_shared = (sizeof(RowData) + sizeof(double) * (1 + P)) * (size_t)c->n_pad;
-  const bool shared_init = shmem_shared + 1024 <= (size_t)c->max_smem_optin;
+  const bool shared_init = jac == fmc::JAC_FD && shmem_shared + 1024 <= (size_t)c->max_smem_optin;
   double* g0_dev = nullptr;
   if (shared_init) {
     const long long need = (long long)(1 + P) * c->n_pad + PP;
@@ -574,8 +592,8 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
       if (call == 0 && shared_init)
         FMC_CUDA(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
       else
-        FMC_CUDA(m.launch_init(a, inject, smem, shmem, c->stream));
-      FMC_CUDA(m.launch_iter(a, inject, smem, (int)grid, shmem, c->stream));
+        FMC_CUDA(m.launch_init(a, inject, smem, jac, shmem, c->stream));
+      FMC_CUDA(m.launch_iter(a, inject, smem, jac, (int)grid, shmem, c->stream));
     }
     if (binning) {
       h.params = a.params_out;
@@ -758,6 +776,7 @@ int bootstrap_run_impl(int model, int ndata, const double* x, const double* y, c
         }
       }
       fmc_set_accumulator_dev(c, nullptr);
+      c->jac = g_default_jac;
       fmc_set_histogram_dev(c, nullptr);
       if ((rc = fmc_set_histogram(c, nbins, bin_lo, bin_hi)) != FMC_OK) break;  // cached context: also switches off
       if ((rc = fmc_launch(c, params_start, cnt, seed, first_counter + lo, zdev, keep ? 1 : 0)) != FMC_OK) break;
@@ -835,6 +854,8 @@ int fmc_fit_once(int model, int ndata, const double* x, const double* y, const d
   FMC_CUDA(cudaMalloc(&zdev, sizeof(double) * ndata));
   FMC_CUDA(cudaMemsetAsync(zdev, 0, sizeof(double) * ndata, c->stream));
   fmc_set_accumulator_dev(c, nullptr);
+  fmc_set_histogram(c, 0, nullptr, nullptr);  // the cached context may have binned before
+  c->jac = g_default_jac;
   rc = fmc_launch(c, params, 1, 0ULL, 0, zdev, 1);
   const int P = models()[model].nparam;
   std::vector<double> pout(P);

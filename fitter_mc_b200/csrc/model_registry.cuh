@@ -16,14 +16,17 @@ struct ModelEntry {
   double init[16];
   double (*model_y)(const double*, double);   // host copies of the plug-in routines
   void (*props)(const double*, double*);
-  // stage A (uniform first pass) and stage B (refill iterations) of one nl2sno call
-  cudaError_t (*launch_init)(const KernelArgs&, bool inject, bool smem, size_t shmem, cudaStream_t);
+  bool analytic;  // can form exact Jacobian rows (generic model_y or its own model_grad)
+  // stage A (uniform first pass) and stage B (refill iterations) of one nl2sno call;
+  // jac = JAC_FD (nl2sno) or JAC_ANALYTIC (nl2sol + madj)
+  cudaError_t (*launch_init)(const KernelArgs&, bool inject, bool smem, int jac, size_t shmem, cudaStream_t);
   // shared-Jacobian variant of stage A for the first call (all fits start at params_start)
   cudaError_t (*launch_jac0)(const KernelArgs&, double* rowJ, double* G0, cudaStream_t);
   cudaError_t (*launch_init_shared)(const KernelArgs&, const double* rowJ, const double* G0, bool inject,
                                     size_t shmem, cudaStream_t);
-  cudaError_t (*launch_iter)(const KernelArgs&, bool inject, bool smem, int grid, size_t shmem, cudaStream_t);
-  cudaError_t (*occupancy)(bool inject, bool smem, size_t shmem, int* blocks_per_sm);
+  cudaError_t (*launch_iter)(const KernelArgs&, bool inject, bool smem, int jac, int grid, size_t shmem,
+                             cudaStream_t);
+  cudaError_t (*occupancy)(bool inject, bool smem, int jac, size_t shmem, int* blocks_per_sm);
 };
 
 template <class M>
@@ -31,25 +34,40 @@ struct ModelBinding {
   static double host_model_y(const double* p, double x) { return M::model_y(p, x); }
   static void host_props(const double* p, double* q) { M::derived_properties(p, q); }
 
-  template <bool INJECT, bool SMEM>
+  static constexpr bool kAnalytic = can_analytic_v<M>;
+
+  template <bool INJECT, bool SMEM, int JAC>
   static cudaError_t prep(size_t shmem) {
-    cudaError_t e = cudaFuncSetAttribute(iterate_kernel<M, INJECT, SMEM>,
+    cudaError_t e = cudaFuncSetAttribute(iterate_kernel<M, INJECT, SMEM, JAC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(init_pass_kernel<M, INJECT, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(init_pass_kernel<M, INJECT, SMEM, JAC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)shmem);
   }
-  // run f(INJECT, SMEM) with the two runtime flags turned into compile-time constants
+  // run f(INJECT, SMEM, JAC) with the runtime flags turned into compile-time constants
   template <class F>
-  static cudaError_t dispatch(bool inject, bool smem, F&& f) {
-    if (inject) return smem ? f(std::true_type{}, std::true_type{}) : f(std::true_type{}, std::false_type{});
-    return smem ? f(std::false_type{}, std::true_type{}) : f(std::false_type{}, std::false_type{});
+  static cudaError_t dispatch(bool inject, bool smem, int jac, F&& f) {
+    using JF = std::integral_constant<int, JAC_FD>;
+    using JA = std::integral_constant<int, JAC_ANALYTIC>;
+    if (jac == JAC_ANALYTIC) {
+      if constexpr (kAnalytic) {
+        if (inject)
+          return smem ? f(std::true_type{}, std::true_type{}, JA{}) : f(std::true_type{}, std::false_type{}, JA{});
+        return smem ? f(std::false_type{}, std::true_type{}, JA{}) : f(std::false_type{}, std::false_type{}, JA{});
+      } else {
+        return cudaErrorNotSupported;  // a double-only model without model_grad has no derivative
+      }
+    }
+    if (inject) return smem ? f(std::true_type{}, std::true_type{}, JF{}) : f(std::true_type{}, std::false_type{}, JF{});
+    return smem ? f(std::false_type{}, std::true_type{}, JF{}) : f(std::false_type{}, std::false_type{}, JF{});
   }
 
-  static cudaError_t launch_init(const KernelArgs& a, bool inject, bool smem, size_t shmem, cudaStream_t st) {
+  static cudaError_t launch_init(const KernelArgs& a, bool inject, bool smem, int jac, size_t shmem,
+                                 cudaStream_t st) {
     const int grid = (int)((a.nres + FMC_THREADS - 1) / FMC_THREADS);
-    return dispatch(inject, smem, [&](auto I, auto S) {
-      init_pass_kernel<M, decltype(I)::value, decltype(S)::value><<<grid, FMC_THREADS, shmem, st>>>(a);
+    return dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
+      init_pass_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>
+          <<<grid, FMC_THREADS, shmem, st>>>(a);
       return cudaGetLastError();
     });
   }
@@ -72,19 +90,20 @@ struct ModelBinding {
     }
     return cudaGetLastError();
   }
-  static cudaError_t launch_iter(const KernelArgs& a, bool inject, bool smem, int grid, size_t shmem,
+  static cudaError_t launch_iter(const KernelArgs& a, bool inject, bool smem, int jac, int grid, size_t shmem,
                                  cudaStream_t st) {
-    return dispatch(inject, smem, [&](auto I, auto S) {
-      iterate_kernel<M, decltype(I)::value, decltype(S)::value><<<grid, FMC_THREADS, shmem, st>>>(a);
+    return dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
+      iterate_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>
+          <<<grid, FMC_THREADS, shmem, st>>>(a);
       return cudaGetLastError();
     });
   }
-  static cudaError_t occupancy(bool inject, bool smem, size_t shmem, int* nb) {
-    return dispatch(inject, smem, [&](auto I, auto S) {
-      cudaError_t e = prep<decltype(I)::value, decltype(S)::value>(shmem);
+  static cudaError_t occupancy(bool inject, bool smem, int jac, size_t shmem, int* nb) {
+    return dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
+      cudaError_t e = prep<decltype(I)::value, decltype(S)::value, decltype(J)::value>(shmem);
       if (e != cudaSuccess) return e;
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          nb, iterate_kernel<M, decltype(I)::value, decltype(S)::value>, FMC_THREADS, shmem);
+          nb, iterate_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>, FMC_THREADS, shmem);
     });
   }
   static ModelEntry entry() {
@@ -100,6 +119,7 @@ struct ModelBinding {
       e.pnames[i] = pn[i];
       e.qnames[i] = qn[i];
     }
+    e.analytic = kAnalytic;
     e.model_y = host_model_y;
     e.props = host_props;
     e.launch_init = launch_init;

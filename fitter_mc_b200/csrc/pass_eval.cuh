@@ -23,6 +23,7 @@
 #include <type_traits>
 #include <utility>
 
+#include "dual.cuh"
 #include "fmc_common.cuh"
 #include "pert.cuh"
 
@@ -40,6 +41,25 @@ constexpr bool use_pert_v = false;  // force the p+1 plain evaluations (validati
 template <class M>
 constexpr bool use_pert_v = has_generic_model<M>::value;
 #endif
+
+// How the Jacobian rows are formed.
+//   JAC_FD        forward differences with nl2sno's steps (toms573.f90:714-733): the reference's path
+//   JAC_ANALYTIC  exact derivatives, what nl2sol + a user madj give (toms573.f90:35-587, README:35-42):
+//                 from the plug-in's own model_grad if it has one, else from the generic model_y
+//                 evaluated on dual numbers (dual.cuh).  The step arrays are then all ones.
+enum { JAC_FD = 0, JAC_ANALYTIC = 1 };
+
+template <class M, class = void>
+struct has_model_grad : std::false_type {};
+template <class M>
+struct has_model_grad<M, std::void_t<decltype(M::model_grad(std::declval<const double*>(), 0.0,
+                                                            std::declval<double*>()))>> : std::true_type {};
+template <class M, class = void>
+struct has_dual_model : std::false_type {};
+template <class M>
+struct has_dual_model<M, std::void_t<decltype(M::model_y(std::declval<const Dual*>(), 0.0))>> : std::true_type {};
+template <class M>
+constexpr bool can_analytic_v = has_model_grad<M>::value || has_dual_model<M>::value;
 
 // An evaluation point with its finite-difference steps, held in registers for a whole pass.
 template <int P>
@@ -80,12 +100,27 @@ struct PassAcc {
 //  * double-only plug-in: p+1 plain evaluations, as nl2sno does (toms573.f90:714-733).  The
 //    model is inlined p+1 times with all but one coordinate identical, so the compiler still
 //    shares common subexpressions (e.g. exp(-al*x) for every column except al's).
-template <class M>
+//  * JAC_ANALYTIC: dm[k] = -d model_y / d params_k (the sign convention of the differences).
+template <class M, int JAC = JAC_FD>
 FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, double& m0,
                                  double (&dm)[M::NPARAM]) {
   constexpr int P = M::NPARAM;
   m0 = M::model_y(pt.x, xi);
-  if constexpr (use_pert_v<M>) {
+  if constexpr (JAC == JAC_ANALYTIC && has_model_grad<M>::value) {
+    double gr[P];
+    M::model_grad(pt.x, xi, gr);
+#pragma unroll
+    for (int kk = 0; kk < P; ++kk) dm[kk] = -gr[kk];
+  } else if constexpr (JAC == JAC_ANALYTIC && has_dual_model<M>::value) {
+#pragma unroll
+    for (int kk = 0; kk < P; ++kk) {
+      Dual xs[P];
+#pragma unroll
+      for (int m = 0; m < P; ++m) xs[m] = Dual(pt.x[m], (m == kk) ? 1.0 : 0.0, m == kk);
+      const Dual mk = M::model_y(xs, xi);
+      dm[kk] = -mk.d;
+    }
+  } else if constexpr (use_pert_v<M>) {
 #pragma unroll
     for (int kk = 0; kk < P; ++kk) {
       Pert xs[P];
@@ -106,12 +141,12 @@ FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, doub
 }
 
 // Add one data point to the pass sums.  WITH_B: also J(b)^T r(a) for the secant update.
-template <class M, bool WITH_B>
+template <class M, bool WITH_B, int JAC = JAC_FD>
 FMC_HD FMC_INLINE void row_accumulate(const PassPoint<M::NPARAM>& a, const PassPoint<M::NPARAM>& b,
                                       double xi, double yfit, double rerr, PassAcc<M::NPARAM>& acc) {
   constexpr int P = M::NPARAM;
   double m0, dma[P];
-  row_model<M>(a, xi, m0, dma);
+  row_model<M, JAC>(a, xi, m0, dma);
   const double r = (yfit - m0) * rerr;  // madr, bootstrap.f90:247
   const double t = rerr * r;
   const double w2 = rerr * rerr;
@@ -129,7 +164,7 @@ FMC_HD FMC_INLINE void row_accumulate(const PassPoint<M::NPARAM>& a, const PassP
   }
   if (WITH_B) {
     double mb, dmb[P];
-    row_model<M>(b, xi, mb, dmb);
+    row_model<M, JAC>(b, xi, mb, dmb);
 #pragma unroll
     for (int i = 0; i < P; ++i) acc.lky[i] = fma(dmb[i], t, acc.lky[i]);
   }
@@ -162,6 +197,19 @@ FMC_HD FMC_INLINE void pass_scale(const PassAcc<P>& acc, const double* hA, const
 template <int P, class Solver>
 FMC_HD FMC_INLINE void pass_finish(const PassAcc<P>& acc, Solver& s) {
   pass_scale<P>(acc, s.hA, s.hJ, s.res_f, s.res_g, s.res_G, s.res_lky);
+}
+
+// The same for an analytic pass: the sums already are J^T r and J^T J, nothing to scale.
+template <int P, class Solver>
+FMC_HD FMC_INLINE void pass_finish_analytic(const PassAcc<P>& acc, Solver& s) {
+  s.res_f = acc.f;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    s.res_g[i] = acc.g[i];
+    s.res_lky[i] = acc.lky[i];
+  }
+#pragma unroll
+  for (int i = 0; i < P * (P + 1) / 2; ++i) s.res_G[i] = acc.G[i];
 }
 
 }  // namespace fmc

@@ -56,6 +56,16 @@ MODULE fmc_b200_bindings
       INTEGER(c_int) :: rc
     END FUNCTION fmc_bootstrap_run_binned
 
+    ! README:35-42 "replace the call to nl2sno with a call to nl2sol": mode 1 fits with exact
+    ! Jacobian rows (the plug-in's model_grad, or dual numbers through its generic model_y).
+    ! ctx = c_null_ptr sets the mode of fmc_bootstrap_run / fmc_fit_once.
+    FUNCTION fmc_set_jacobian_mode(ctx, mode) BIND(C, name='fmc_set_jacobian_mode') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr), VALUE :: ctx
+      INTEGER(c_int), VALUE :: mode
+      INTEGER(c_int) :: rc
+    END FUNCTION fmc_set_jacobian_mode
+
     ! Quantiles of one quantity from its column of counts.
     FUNCTION fmc_histogram_quantiles(counts, nbins, lo, hi, probs, nprobs, out) &
       &BIND(C, name='fmc_histogram_quantiles') RESULT(outside)

@@ -129,6 +129,21 @@ int fmc_decode_accumulator(int model, const double* params_start, const double* 
  * step recomputation, bit3 passes; bits 8+ = which nl2sno call).  Call after fmc_finish/fmc_wait. */
 int fmc_last_anomalies(fmc_context* ctx, long long* ids, int* flags, int cap);
 
+/* ---- analytic Jacobian ----------------------------------------------
+ * The reference fits with nl2sno, which differences the residuals (toms573.f90:590-769), and
+ * tells users who want analytic derivatives to write a `madj` and call nl2sol instead
+ * (README:35-42; toms573.f90:35-587).  FMC_JACOBIAN_ANALYTIC is that switch: the same NL2SOL
+ * iteration fed with exact Jacobian rows, taken from the plug-in's model_grad if it has one,
+ * else from its generic model_y by dual numbers (csrc/dual.cuh).  Opt-in, because results
+ * move at the 1e-8 level relative to the forward-difference path (the size of the forward-
+ * difference truncation error).  ctx = NULL sets the mode of the one-call entry points
+ * (fmc_bootstrap_run, fmc_bootstrap_run_binned, fmc_fit_once).  A launch in analytic mode on
+ * a model without derivatives fails with FMC_ERR_BAD_ARG. */
+#define FMC_JACOBIAN_FORWARD_DIFFERENCE 0
+#define FMC_JACOBIAN_ANALYTIC 1
+int fmc_set_jacobian_mode(fmc_context* ctx, int mode);
+int fmc_model_has_analytic_jacobian(int model);
+
 /* ---- binned distributions -------------------------------------------
  * Replaces the reference's histogram_<prop>.dat dumps -- one list-directed text line per
  * resample and property, written inside an OMP CRITICAL (bootstrap.f90:301-308, 319-325,

@@ -63,6 +63,48 @@ inline double model_y(int model, const double* p, double x) {
   }
 }
 
+// Partial derivatives of model_y with respect to the parameters, derived by hand (the `madj`
+// a user of nl2sol would write, README:35-42).
+inline void model_grad(int model, const double* p, double x, double* g) {
+  switch (model) {
+    case 0: {
+      const double e = std::exp(-p[2] * x);
+      g[0] = 1.0;
+      g[1] = e;
+      g[2] = -p[1] * x * e;
+      break;
+    }
+    case 1: {
+      const double e = std::exp(-p[2] * x);
+      g[0] = 1.0;
+      g[1] = e;
+      g[2] = -p[1] * x * e;
+      g[3] = x;
+      break;
+    }
+    case 2:
+      g[0] = 1.0;
+      for (int k = 0; k < 3; ++k) {
+        const double A = p[1 + 3 * k], mu = p[2 + 3 * k], w = p[3 + 3 * k];
+        const double u = (x - mu) / w, gs = std::exp(-0.5 * (u * u));
+        g[1 + 3 * k] = gs;
+        g[2 + 3 * k] = A * gs * u / w;
+        g[3 + 3 * k] = A * gs * u * u / w;
+      }
+      break;
+    case 3: {
+      const double e = std::exp(-p[1] * x), pw = std::pow(x, -p[3]);
+      g[0] = e;
+      g[1] = -p[0] * x * e;
+      g[2] = pw;
+      g[3] = -p[2] * pw * std::log(x);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
 inline void derived_properties(int model, const double* p, double* props) {
   switch (model) {
     case 0:  // bootstrap.f90:406
@@ -98,6 +140,17 @@ void madr(int n, int p, const double* params, int* nf, double* r, void* vctx) {
   c->neval++;
 }
 
+// madj: d r_i / d params_k = -(d model_y / d params_k) / err_i, column-major (toms573.f90:57-66)
+void madj(int n, int p, const double* params, int* nf, double* j, void* vctx) {
+  (void)nf;
+  FitCtx* c = (FitCtx*)vctx;
+  double g[FMC_ORACLE_MAX_P];
+  for (int i = 0; i < n; ++i) {
+    model_grad(c->model, params, c->x[i], g);
+    for (int k = 0; k < p; ++k) j[(size_t)k * n + i] = -g[k] * c->rerr[i];
+  }
+}
+
 struct Workspace {
   std::vector<int> iv;
   std::vector<double> v;
@@ -120,7 +173,10 @@ void fit_data(FitCtx& ctx, int n, int p, double* params, int flags, Workspace& w
       iv[14 - 1] = 0;
       iv[15 - 1] = 0;
     }
-    nl2::nl2sno(n, p, params, madr, iv, v, &ctx, opt);
+    if (flags & FMC_ORACLE_ANALYTIC_JAC)
+      nl2::nl2sol(n, p, params, madr, madj, iv, v, &ctx, opt);
+    else
+      nl2::nl2sno(n, p, params, madr, iv, v, &ctx, opt);
     if (counters) {
       int* c = counters + pass * FMC_ORACLE_NCOUNTERS;
       c[0] = iv[0];
@@ -170,6 +226,15 @@ void fmc_oracle_derived_properties(int model, const double* params, double* prop
 void fmc_oracle_madr(int model, int n, const double* x, const double* y_fit, const double* err,
                      const double* params, double* r) {
   for (int i = 0; i < n; ++i) r[i] = (y_fit[i] - model_y(model, params, x[i])) * (1.0 / err[i]);
+}
+
+void fmc_oracle_madj(int model, int n, const double* x, const double* err, const double* params, double* j) {
+  const int p = kModels[model].nparam;
+  double g[FMC_ORACLE_MAX_P];
+  for (int i = 0; i < n; ++i) {
+    model_grad(model, params, x[i], g);
+    for (int k = 0; k < p; ++k) j[(size_t)k * n + i] = -g[k] * (1.0 / err[i]);
+  }
 }
 
 int fmc_oracle_fit_data(int model, int n, const double* x, const double* y_fit, const double* err,

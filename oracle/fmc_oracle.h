@@ -42,6 +42,8 @@ void fmc_oracle_derived_properties(int model, const double* params, double* prop
 #define FMC_ORACLE_LSVMIN_PER_FIT 4 /* reset lsvmin's LCG to 2 at the start of each fit (order-independent results) */
 #define FMC_ORACLE_HISTOGRAM 8    /* write props to /dev/null-like text sink under a critical section (cost model of bootstrap.f90:319-325) */
 
+#define FMC_ORACLE_ANALYTIC_JAC 16 /* fit with nl2sol + an analytic madj instead of nl2sno (README:35-42) */
+
 /* counters[pass][k]: k = 0 iv(1) return code, 1 nfcall, 2 ngcall, 3 niter, 4 nfcov, 5 ngcov */
 #define FMC_ORACLE_NCOUNTERS 6
 
@@ -52,6 +54,11 @@ int fmc_oracle_fit_data(int model, int n, const double* x, const double* y_fit, 
 /* residual vector madr (bootstrap.f90:229-250) and chi^2 (bootstrap.f90:452-458) */
 void fmc_oracle_madr(int model, int n, const double* x, const double* y_fit, const double* err,
                      const double* params, double* r);
+
+/* madj: the analytic Jacobian of madr, j[k*n + i] = d r_i / d params_k (what README:35-42
+ * asks a user of nl2sol to write), from hand-derived formulas for the compiled-in models. */
+void fmc_oracle_madj(int model, int n, const double* x, const double* err, const double* params,
+                     double* j);
 
 /* rng_mode for the bootstrap loop */
 #define FMC_ORACLE_RNG_RANLUX 0   /* the reference's serial RANLUX+polar stream (state = the global generator) */

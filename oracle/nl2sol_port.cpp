@@ -2170,4 +2170,51 @@ L100:
   return;
 }
 
+// ---------------------------------------------------------------- nl2sol
+// toms573.f90:35-587 (executable part 512-551).  Same reverse-communication loop as nl2sno
+// with the finite-difference block replaced by one call of the user's calcj.
+void nl2sol(int n, int p, double* x, calcr_fn calcr, calcj_fn calcj, int* iv, double* v, void* ctx,
+            const Options& opt) {
+  bool strted;
+  int d1, j1, nf, r1;
+
+  d1 = 94 + 2 * n + p * (3 * p + 31) / 2;  // :512
+  IV(IV_D) = d1;
+  r1 = d1 + p;
+  IV(IV_R) = r1;
+  j1 = r1 + n;
+  IV(IV_J) = j1;
+  strted = true;
+  if (IV(1) != 0 && IV(1) != 12) goto L40;  // :519
+  strted = false;
+  IV(NFCALL) = 1;
+  IV(NFGCAL) = 1;
+
+L10:
+  nf = IV(NFCALL);
+  calcr(n, p, x, &nf, &V(r1), ctx);
+  if (strted) goto L20;
+  if (nf > 0) goto L30;
+  IV(1) = 13;
+  goto L70;  // :528-529 (itsmry prints only)
+L20:
+  if (nf <= 0) IV(TOOBIG) = 1;
+  goto L40;
+
+L30:
+  calcj(n, p, x, &IV(NFGCAL), &V(j1), ctx);  // :535
+  if (IV(NFGCAL) == 0) {
+    IV(1) = 15;
+    goto L70;
+  }
+  strted = true;
+
+L40:
+  nl2itr(&V(d1), iv, &V(j1), n, n, p, &V(r1), v, x, opt);
+  if (IV(1) < 2) goto L10;
+  if (IV(1) == 2) goto L30;
+L70:
+  return;
+}
+
 }  // namespace nl2

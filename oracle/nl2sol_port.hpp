@@ -36,6 +36,13 @@ inline int v_len(int n, int p) { return 93 + n * (p + 3) + p * (3 * p + 33) / 2;
 void dfault(int* iv, double* v);                                   // toms573.f90:2337-2400
 void nl2sno(int n, int p, double* x, calcr_fn calcr, int* iv, double* v, void* ctx,
             const Options& opt);                                   // toms573.f90:590-769
+// calcj callback, toms573.f90:57-66: j(i,k) = d r_i / d x_k, column-major n x p.  nf = 0 on
+// return means "Jacobian cannot be computed at x".
+typedef void (*calcj_fn)(int n, int p, const double* x, int* nf, double* j, void* ctx);
+// The analytic-Jacobian driver the reference's README (35-42) points users to ("introduce a
+// subroutine madj ... and replace the call to nl2sno with a call to nl2sol").
+void nl2sol(int n, int p, double* x, calcr_fn calcr, calcj_fn calcj, int* iv, double* v, void* ctx,
+            const Options& opt);                                   // toms573.f90:35-587
 
 // exposed for unit tests
 double dotprd(int p, const double* x, const double* y);            // :2403

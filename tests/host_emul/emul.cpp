@@ -18,7 +18,7 @@ using namespace fmc;
 
 namespace {
 
-template <class M>
+template <class M, int JAC = JAC_FD>
 void run_pass(Nl2<M::NPARAM>& s, int n, const double* x, const double* yfit, const double* rerr) {
   constexpr int P = M::NPARAM;
   PassPoint<P> a, b;
@@ -28,15 +28,18 @@ void run_pass(Nl2<M::NPARAM>& s, int n, const double* x, const double* yfit, con
   acc.zero();
   for (int i = 0; i < n; ++i) {
     if (s.need_b)
-      row_accumulate<M, true>(a, b, x[i], yfit[i], rerr[i], acc);
+      row_accumulate<M, true, JAC>(a, b, x[i], yfit[i], rerr[i], acc);
     else
-      row_accumulate<M, false>(a, b, x[i], yfit[i], rerr[i], acc);
+      row_accumulate<M, false, JAC>(a, b, x[i], yfit[i], rerr[i], acc);
   }
-  pass_finish<P>(acc, s);
+  if constexpr (JAC == JAC_ANALYTIC)
+    pass_finish_analytic<P>(acc, s);
+  else
+    pass_finish<P>(acc, s);
 }
 
 // counters[pass][0..3] = rc, nfcall, ngcall, niter ; counters[pass][4] = passes over the data
-template <class M>
+template <class M, int JAC = JAC_FD>
 int fit_one(int n, const double* x, const double* yfit, const double* err, double* params,
             int* counters, int* anomaly_out = nullptr) {
   constexpr int P = M::NPARAM;
@@ -49,7 +52,7 @@ int fit_one(int n, const double* x, const double* yfit, const double* err, doubl
     s.begin(params);
     int npass = 0;
     for (;;) {
-      run_pass<M>(s, n, x, yfit, rerr.data());
+      run_pass<M, JAC>(s, n, x, yfit, rerr.data());
       ++npass;
       if (!s.resume()) break;
       if (npass > 2 * (k::mxfcal + k::mxiter)) {  // the kernel's cap on passes per call
@@ -72,7 +75,7 @@ int fit_one(int n, const double* x, const double* yfit, const double* err, doubl
   return 0;
 }
 
-template <class M>
+template <class M, int JAC = JAC_FD>
 int bootstrap(int n, const double* x, const double* y, const double* err, const double* start,
               long long nres, const double* z, unsigned long long seed, long long first,
               double* params_out, double* props_out, int* counters_out, int* anomalies_out = nullptr) {
@@ -90,7 +93,7 @@ int bootstrap(int n, const double* x, const double* y, const double* err, const 
     }
     for (int i = 0; i < P; ++i) p[i] = start[i];
     int anom = 0;
-    fit_one<M>(n, x, yfit.data(), err, p.data(), counters_out ? counters_out + 10 * r : nullptr, &anom);
+    fit_one<M, JAC>(n, x, yfit.data(), err, p.data(), counters_out ? counters_out + 10 * r : nullptr, &anom);
     if (anomalies_out) anomalies_out[r] = anom;
     std::memcpy(params_out + (size_t)r * P, p.data(), sizeof(double) * P);
     if (props_out) M::derived_properties(p.data(), props_out + (size_t)r * Q);
@@ -116,9 +119,82 @@ void row_model_both(const double* x, const double* h, double xi, double* m0, dou
   }
 }
 
+// d model_y / d params_k as the analytic path forms it (dual numbers or the plug-in's model_grad)
+template <class M>
+void row_grad(const double* x, double xi, double* grad) {
+  constexpr int P = M::NPARAM;
+  double ones[P];
+  for (int i = 0; i < P; ++i) ones[i] = 1.0;
+  PassPoint<P> pt;
+  pt.set(x, ones);
+  double m0, dm[P];
+  row_model<M, JAC_ANALYTIC>(pt, xi, m0, dm);
+  for (int i = 0; i < P; ++i) grad[i] = -dm[i];
+}
+
+// A double-only plug-in WITH its own madj (model_grad), and one without any derivative.
+struct ModelHandGrad {
+  static constexpr int NPARAM = 3;
+  static constexpr int NPROP = 1;
+  static double model_y(const double* p, double x) { return p[0] + p[1] * std::exp(-p[2] * x); }
+  static void model_grad(const double* p, double x, double* g) {
+    const double e = std::exp(-p[2] * x);
+    g[0] = 1.0;
+    g[1] = e;
+    g[2] = -p[1] * x * e;
+  }
+  static void derived_properties(const double* p, double* q) { q[0] = p[0] + p[1]; }
+};
+struct ModelPlainOnly {
+  static constexpr int NPARAM = 3;
+  static constexpr int NPROP = 1;
+  static double model_y(const double* p, double x) { return p[0] + p[1] * std::exp(-p[2] * x); }
+  static void derived_properties(const double* p, double* q) { q[0] = p[0] + p[1]; }
+};
+static_assert(can_analytic_v<ModelUser> && can_analytic_v<ModelTest4> && can_analytic_v<ModelPeaks10> &&
+                  can_analytic_v<ModelStiff4>,
+              "the compiled-in models are generic, so they have dual-number derivatives");
+static_assert(has_model_grad<ModelHandGrad>::value && !has_dual_model<ModelHandGrad>::value &&
+                  can_analytic_v<ModelHandGrad>,
+              "a plug-in's own model_grad is detected");
+static_assert(!can_analytic_v<ModelPlainOnly> && !use_pert_v<ModelPlainOnly>, "double-only model: no derivative");
+
 }  // namespace
 
 extern "C" {
+
+// jac = 0: forward differences (nl2sno), 1: analytic (nl2sol + madj).  model 100 = the
+// double-only test plug-in with a hand-written model_grad (same formula as model 0).
+int emul_bootstrap_jac(int model, int jac, int n, const double* x, const double* y, const double* err,
+                       const double* start, long long nres, const double* z, double* params_out, double* props_out,
+                       int* counters_out, int* anomalies_out) {
+#define EMUL_CASE(ID, M)                                                                                          \
+  case ID:                                                                                                        \
+    return jac ? bootstrap<M, JAC_ANALYTIC>(n, x, y, err, start, nres, z, 0, 0, params_out, props_out,            \
+                                            counters_out, anomalies_out)                                          \
+               : bootstrap<M, JAC_FD>(n, x, y, err, start, nres, z, 0, 0, params_out, props_out, counters_out,   \
+                                      anomalies_out);
+  switch (model) {
+    EMUL_CASE(0, ModelUser)
+    EMUL_CASE(1, ModelTest4)
+    EMUL_CASE(2, ModelPeaks10)
+    EMUL_CASE(3, ModelStiff4)
+    EMUL_CASE(100, ModelHandGrad)
+  }
+#undef EMUL_CASE
+  return -1;
+}
+
+int emul_row_grad(int model, const double* x, double xi, double* grad) {
+  switch (model) {
+    case 0: row_grad<ModelUser>(x, xi, grad); return 0;
+    case 1: row_grad<ModelTest4>(x, xi, grad); return 0;
+    case 2: row_grad<ModelPeaks10>(x, xi, grad); return 0;
+    case 3: row_grad<ModelStiff4>(x, xi, grad); return 0;
+    case 100: row_grad<ModelHandGrad>(x, xi, grad); return 0;
+  }
+  return -1;
+}
 
 int emul_fit(int model, int n, const double* x, const double* yfit, const double* err, double* params,
              int* counters) {

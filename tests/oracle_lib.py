@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "libfmc_oracle.so")
 
-COVARIANCE, COPY_JAC, LSVMIN_PER_FIT, HISTOGRAM = 1, 2, 4, 8
+COVARIANCE, COPY_JAC, LSVMIN_PER_FIT, HISTOGRAM, ANALYTIC_JAC = 1, 2, 4, 8, 16
 RNG_RANLUX, RNG_INJECT = 0, 1
 NCOUNTERS = 6
 
@@ -47,6 +47,7 @@ def lib():
         L.fmc_oracle_initialise_model.argtypes = [C.c_int, _ip, _ip, _dp, C.c_void_p, C.c_void_p, C.c_char_p]
         L.fmc_oracle_fit_data.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _ip]
         L.fmc_oracle_madr.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.fmc_oracle_madj.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.fmc_oracle_bootstrap.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, C.c_int, _dp,
                                            C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _lp, _lp]
         L.fmc_oracle_finalise_moments.argtypes = [C.c_int, C.c_longlong, _dp, _dp, _dp, _dp]
@@ -118,6 +119,14 @@ def madr(model, x, y_fit, err, params):
     r = np.empty(len(x))
     lib().fmc_oracle_madr(model, len(x), _d(x), _d(y_fit), _d(err), _d(params), _d(r))
     return r
+
+
+def madj(model, x, err, params):
+    """Analytic Jacobian of madr, [n][p] (hand-derived formulas, the user's `madj` of README:35-42)."""
+    x, err, params = map(_f64, (x, err, params))
+    j = np.empty((len(params), len(x)))
+    lib().fmc_oracle_madj(model, len(x), _d(x), _d(err), _d(params), _d(j))
+    return j.T.copy()
 
 
 def fit_data(model, x, y_fit, err, params, flags=LSVMIN_PER_FIT):
