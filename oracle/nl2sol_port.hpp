@@ -11,7 +11,9 @@
 // is pinned instead by (i) routine-by-routine review against toms573.f90
 // (file:line cited at every routine), (ii) agreement with scipy/MINPACK on
 // identical data (tests/test_oracle_solver.py), (iii) the mcfit.py probe
-// numbers in BASELINE.md.  The RANLUX part IS pinned by ranlux.f:399-473.
+// numbers in BASELINE.md and golden vectors generated from mcfit.py
+// (tests/golden), (iv) the published minima of ten classical test problems
+// (tests/test_classic_problems.py).  The RANLUX part IS pinned by ranlux.f:399-473.
 //
 // Layout convention: the reference's 1-based IV()/V() maps (SURVEY.md
 // Appendix B) are kept so every index constant can be checked by eye.

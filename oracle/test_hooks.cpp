@@ -75,4 +75,47 @@ int fmc_oracle_tr_step(int model, int n, int p, const double* jac, const double*
   return 0;
 }
 
+
+// nl2sno on an arbitrary residual function supplied by the test (ctypes callback), called the
+// way fit_data calls it (bootstrap.f90:219-225: dfault, silent, `ncalls` calls in a row, each
+// restarting from the previous answer).  Lets the tests run the classical least-squares test
+// problems with known minima (More, Garbow & Hillstrom 1981 -- the set the NL2SOL paper uses)
+// through the restatement.  counters[call][0..3] = iv(1), nfcall, ngcall, niter; fval = v(f)
+// = half the sum of squares at the final point.
+typedef void (*fmc_resid_cb)(int n, int p, const double* x, double* r);
+
+namespace {
+struct CbCtx {
+  fmc_resid_cb cb;
+};
+void cb_calcr(int n, int p, const double* x, int* nf, double* r, void* vctx) {
+  (void)nf;
+  ((CbCtx*)vctx)->cb(n, p, x, r);
+}
+}  // namespace
+
+int fmc_oracle_nl2sno_generic(int n, int p, double* x, fmc_resid_cb cb, int ncalls, int* counters, double* fval) {
+  std::vector<int> iv(nl2::iv_len(p));
+  std::vector<double> v(nl2::v_len(n, p));
+  CbCtx ctx{cb};
+  nl2::Options opt;
+  opt.copy_jac = false;
+  int ix = 2;
+  opt.lsvmin_ix = &ix;
+  for (int call = 0; call < ncalls; ++call) {
+    nl2::dfault(iv.data(), v.data());
+    for (int k = 19; k <= 24; ++k) iv[k - 1] = 0;
+    iv[14 - 1] = 0;  // covprt, covreq: no covariance (dead work on this path)
+    iv[15 - 1] = 0;
+    nl2::nl2sno(n, p, x, cb_calcr, iv.data(), v.data(), &ctx, opt);
+    if (counters) {
+      counters[4 * call + 0] = iv[0];
+      counters[4 * call + 1] = iv[6 - 1];
+      counters[4 * call + 2] = iv[30 - 1];
+      counters[4 * call + 3] = iv[31 - 1];
+    }
+  }
+  if (fval) *fval = v[10 - 1];  // v(f)
+  return 0;
+}
 }  // extern "C"

@@ -13,6 +13,7 @@
 #include "../../fitter_mc_b200/csrc/nl2_solver.cuh"
 #include "../../fitter_mc_b200/csrc/pass_eval.cuh"
 #include "../../fitter_mc_b200/csrc/rng.cuh"
+#include "mgh_models.hpp"
 
 using namespace fmc;
 
@@ -182,6 +183,32 @@ int emul_bootstrap_jac(int model, int jac, int n, const double* x, const double*
     EMUL_CASE(100, ModelHandGrad)
   }
 #undef EMUL_CASE
+  return -1;
+}
+
+// One fit_data (two solver calls) of the product's solver on a classical test problem
+// (mgh_models.hpp), jac = 0 forward differences / 1 analytic.  counters: [2][5].
+int emul_fit_classic(int problem, int jac, int n, const double* t, const double* y, double* params, int* counters,
+                     int* anomaly) {
+  std::vector<double> err(n, 1.0);
+  *anomaly = 0;
+#define MGH_CASE(ID, M)                                                                       \
+  case ID:                                                                                    \
+    return jac ? fit_one<M, JAC_ANALYTIC>(n, t, y, err.data(), params, counters, anomaly)     \
+               : fit_one<M, JAC_FD>(n, t, y, err.data(), params, counters, anomaly);
+  switch (problem) {
+    MGH_CASE(0, MghRosenbrock)
+    MGH_CASE(1, MghPowellSingular)
+    MGH_CASE(2, MghFreudensteinRoth)
+    MGH_CASE(3, MghBard)
+    MGH_CASE(4, MghKowalikOsborne)
+    MGH_CASE(5, MghMeyer)
+    MGH_CASE(6, MghOsborne1)
+    MGH_CASE(7, MghBox3D)
+    MGH_CASE(8, MghBrownDennis)
+    MGH_CASE(9, MghJennrichSampson)
+  }
+#undef MGH_CASE
   return -1;
 }
 
