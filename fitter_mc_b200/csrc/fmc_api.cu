@@ -40,6 +40,14 @@ int g_default_jac = 0;  // Jacobian mode of the one-call entry points (fmc_set_j
     }                                                                                    \
   } while (0)
 
+// temporary device buffer, released on every return path
+struct DevBuf {
+  double* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
 const std::vector<ModelEntry>& models() {
   static const std::vector<ModelEntry> m = {fmc::fmc_entry_model0(), fmc::fmc_entry_model1(),
                                             fmc::fmc_entry_model2(), fmc::fmc_entry_model3()};
@@ -850,8 +858,9 @@ int fmc_fit_once(int model, int ndata, const double* x, const double* y, const d
   if (rc != FMC_OK) return rc;
   if ((rc = fmc_set_data(c, model, ndata, x, y, err_y)) != FMC_OK) return rc;
   // offset_data(.FALSE.): a single "resample" with all offsets zero
-  double* zdev = nullptr;
-  FMC_CUDA(cudaMalloc(&zdev, sizeof(double) * ndata));
+  DevBuf zbuf;
+  FMC_CUDA(cudaMalloc(&zbuf.p, sizeof(double) * ndata));
+  double* zdev = zbuf.p;
   FMC_CUDA(cudaMemsetAsync(zdev, 0, sizeof(double) * ndata, c->stream));
   fmc_set_accumulator_dev(c, nullptr);
   fmc_set_histogram(c, 0, nullptr, nullptr);  // the cached context may have binned before
@@ -861,7 +870,6 @@ int fmc_fit_once(int model, int ndata, const double* x, const double* y, const d
   std::vector<double> pout(P);
   int cnt[10];
   if (rc == FMC_OK) rc = fmc_finish(c, nullptr, nullptr, nullptr, nullptr, pout.data(), nullptr, cnt, nullptr, nullptr);
-  cudaFree(zdev);
   if (rc != FMC_OK) return rc;
   for (int i = 0; i < P; ++i) params[i] = pout[i];
   if (rc2) {
@@ -878,11 +886,19 @@ int fmc_measure_dfma_peak(int device, int iters, double* tflops, float* ms_out) 
   cudaDeviceProp prop;
   FMC_CUDA(cudaGetDeviceProperties(&prop, device));
   const int threads = 256, blocks = prop.multiProcessorCount * 8;
-  double* out = nullptr;
-  FMC_CUDA(cudaMalloc(&out, sizeof(double) * threads * blocks));
-  cudaEvent_t e0, e1;
-  FMC_CUDA(cudaEventCreate(&e0));
-  FMC_CUDA(cudaEventCreate(&e1));
+  DevBuf obuf;
+  FMC_CUDA(cudaMalloc(&obuf.p, sizeof(double) * threads * blocks));
+  double* out = obuf.p;
+  struct Events {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } ev;
+  FMC_CUDA(cudaEventCreate(&ev.a));
+  FMC_CUDA(cudaEventCreate(&ev.b));
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   dfma_peak_kernel<<<blocks, threads>>>(out, iters / 8 + 1, 0.999999, 1e-6);  // warm-up
   FMC_CUDA(cudaEventRecord(e0));
   dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-6);
@@ -890,9 +906,6 @@ int fmc_measure_dfma_peak(int device, int iters, double* tflops, float* ms_out) 
   FMC_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   FMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(out);
   const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
   *tflops = flops / (ms * 1e-3) / 1e12;
   if (ms_out) *ms_out = ms;
@@ -907,14 +920,14 @@ int fmc_generate_offsets(unsigned long long seed, long long first_counter, long 
   fmc_context* c = nullptr;
   int rc = cached_context(0, &c);
   if (rc != FMC_OK) return rc;
-  double* zdev = nullptr;
-  FMC_CUDA(cudaMalloc(&zdev, sizeof(double) * (size_t)nresample * ndata));
+  DevBuf zbuf;
+  FMC_CUDA(cudaMalloc(&zbuf.p, sizeof(double) * (size_t)nresample * ndata));
+  double* zdev = zbuf.p;
   generate_offsets_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(seed, first_counter, nresample, ndata, zdev);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(z_out, zdev, sizeof(double) * (size_t)nresample * ndata, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(zdev);
   if (e != cudaSuccess) {
     g_last_cuda_error = std::string("generate_offsets: ") + cudaGetErrorString(e);
     return FMC_ERR_CUDA;
