@@ -8,11 +8,20 @@ import datasets, oracle_lib as oracle
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 nres = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+mode = sys.argv[4] if len(sys.argv) > 4 else "fd"        # "fd", "analytic", "analytic+binned", "fd+binned"
 model, x, y, err = datasets.dataset(name)
 info = oracle.model_info(model)
 start, _ = oracle.fit_data(model, x, y, err, info["params_init"])
 ctx = fmc.Context(0)
 ctx.set_data(model, x, y, err)
+if "analytic" in mode:
+    ctx.set_jacobian_mode("analytic")
+if "binned" in mode:
+    import numpy as np
+    ctx.launch(start, 4096, keep=True)
+    pilot = ctx.finish()
+    lo, hi = fmc.histogram_range_from_pilot(np.column_stack([pilot["params"], pilot["props"]]))
+    ctx.set_histogram(1024, lo, hi)
 for rep in range(reps):
     ctx.launch(start, nres, first_counter=rep * nres)
     out = ctx.finish()
