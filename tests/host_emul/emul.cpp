@@ -212,6 +212,27 @@ int emul_fit_classic(int problem, int jac, int n, const double* t, const double*
   return -1;
 }
 
+// The product's gqtstp on a given scaled Hessian H = D^-1 (J^T J + S) D^-1 (packed lower triangle
+// by rows), scaled gradient dig and radius, from a fresh start (ka = -1), p = 2.
+int emul_gqtstp2(const double* hmat, const double* dig, const double* d, double radius, double* step,
+                 int* ka_out, int* anomaly_out) {
+  Nl2<2> s;
+  std::memset(&s, 0, sizeof(s));
+  s.reset_fit();
+  for (int i = 0; i < 3; ++i) s.hmat[i] = hmat[i];
+  for (int i = 0; i < 2; ++i) {
+    s.dig[i] = dig[i];
+    s.d[i] = d[i];
+  }
+  s.v[Nl2<2>::RADIUS] = radius;
+  s.kagqt = -1;
+  s.gqtstp();
+  for (int i = 0; i < 2; ++i) step[i] = s.step[i];
+  *ka_out = s.kagqt;
+  *anomaly_out = s.anomaly;
+  return 0;
+}
+
 int emul_row_grad(int model, const double* x, double xi, double* grad) {
   switch (model) {
     case 0: row_grad<ModelUser>(x, xi, grad); return 0;

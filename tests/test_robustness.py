@@ -84,3 +84,66 @@ def test_degenerate_inputs_terminate(emul, case):
     assert (co[:, :, 4] <= 2 * (200 + 150)).all()
     if case in ("constant_y", "n_equals_p", "zero_param_column"):
         assert np.isfinite(po).all()
+
+
+_SPIN_CHILD = r"""
+import signal, sys
+sys.path.insert(0, %(tests)r)
+import ctypes as C
+import numpy as np
+import oracle_lib as O
+dp = C.POINTER(C.c_double)
+L = O.lib()
+L.fmc_oracle_tr_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, dp, dp,
+                                 C.POINTER(C.c_int)]
+eps = %(eps)r
+# H = D^-1 (J^T J + S) D^-1 = diag(-1, 1), gradient g = J^T r = (eps^2, 0), radius 1
+jac = np.array([eps, 0.0, 0.0, 0.0]); r = np.array([eps, 0.0]); d = np.ones(2); S = np.array([-1.0 - eps * eps, 0.0, 1.0])
+step = np.zeros(2); v = np.zeros(9); ka = C.c_int(0)
+D = lambda a: a.ctypes.data_as(dp)
+print("start", flush=True)
+signal.signal(signal.SIGALRM, signal.SIG_DFL)
+signal.alarm(3)                                   # the default action kills the process inside the C call
+L.fmc_oracle_tr_step(2, 2, 2, D(jac), D(r), D(d), D(S), 1.0, 0.0, 0.0, D(step), D(v), C.byref(ka))
+signal.alarm(0)
+print("returned", step.tolist(), ka.value, flush=True)
+"""
+
+
+def test_gqtstp_retry_loop_of_the_reference_has_no_bound_and_the_product_caps_it(emul):
+    """The mechanism behind the one-in-3e7 GPU hang, reproduced on the CPU.
+
+    gqtstp's retry after a failed Cholesky factorisation (toms573.f90:2828-2856, label 200) has no
+    iteration limit.  With an indefinite H and a gradient that is negligible against its most
+    negative eigenvalue -- the noise-level last iteration of a fit -- the upper bound
+    uk = |g|/rad - emin rounds to -emin whenever the Gerschgorin estimate is tight, the safeguard
+    sets alphak = uk * sqrt(lk/uk) = uk, H + uk I is singular to rounding, the factorisation fails
+    with a zero pivot, lk := alphak, and the loop repeats with identical numbers for ever.  The
+    restatement of the reference algorithm (the oracle) therefore never returns on
+    H = diag(-1, 1), |g| = 1e-30; the product's solver leaves after 150 retries, flags the fit
+    (anomaly bit 1) and returns a finite step."""
+    import signal
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    # sanity: with a gradient that matters the oracle's step returns and has the radius' length
+    ok = subprocess.run([sys.executable, "-c", _SPIN_CHILD % dict(tests=here, eps=1e-3)], capture_output=True,
+                        text=True, timeout=120)
+    assert ok.returncode == 0 and "returned [-0.99999999" in ok.stdout, ok.stdout + ok.stderr
+    spin = subprocess.run([sys.executable, "-c", _SPIN_CHILD % dict(tests=here, eps=1e-15)], capture_output=True,
+                          text=True, timeout=120)
+    assert "start" in spin.stdout and "returned" not in spin.stdout
+    assert spin.returncode == -signal.SIGALRM                     # still inside the loop after 3 s
+
+    emul.emul_gqtstp2.argtypes = [C.POINTER(C.c_double)] * 3 + [C.c_double, C.POINTER(C.c_double),
+                                                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    h, d = np.array([-1.0, 0.0, 1.0]), np.ones(2)
+    for g0, capped in ((1e-30, True), (1e-16, True), (1e-6, False)):
+        dig, step = np.array([g0, 0.0]), np.zeros(2)
+        ka, an = C.c_int(0), C.c_int(0)
+        emul.emul_gqtstp2(_d(h), _d(dig), _d(d), 1.0, _d(step), C.byref(ka), C.byref(an))
+        assert np.isfinite(step).all() and np.linalg.norm(step) <= 1.1
+        assert (an.value == 2 and ka.value == 150) if capped else (an.value == 0 and ka.value < 12)
+        if not capped:
+            assert np.allclose(step, [-1.0, 0.0])                 # along the negative-curvature direction
