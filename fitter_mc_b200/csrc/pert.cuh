@@ -9,8 +9,8 @@
 // the one perturbed parameter moves by its step h.  Every operation propagates d with the
 // exact algebraic identity where one exists (+, -, *, /) and with a Taylor expansion in the
 // tiny relative perturbation that is exact to working precision otherwise (exp, log, pow,
-// sqrt, sin, cos: fourth order, relative truncation error of d below 1e-16 for the step sizes
-// NL2SOL uses).  The result's d is therefore
+// sqrt, sin, cos: relative truncation error of d below 1e-16 for the step sizes NL2SOL uses;
+// see expm1_small below).  The result's d is therefore
 //     m(x + h_k e_k) - m(x)
 // -- the very numerator of the reference's forward difference, with the SAME h and hence the
 // same O(h f'') truncation error; this is not analytic differentiation -- but obtained
@@ -84,14 +84,31 @@ FMC_HD FMC_INLINE Pert operator/(const Pert& a, double b) { return Pert(a.v / b,
 FMC_HD FMC_INLINE Pert operator/(double a, const Pert& b) { return Pert(a) / b; }
 
 // ---- expansions in the tiny perturbation -------------------------------------------------
-// expm1(t) and log1p(u) for the tiny arguments that arise here (|t| ~ 1e-8 with NL2SOL's steps):
-// branch-free 4-term series, relative truncation error t^4/120 (< 1e-10 up to |t| = 1e-2; with
-// h ~ 1.5e-8 |x_k| such a perturbation would need a model argument of order 1e6).
+// expm1(t) and log1p(u) for the tiny arguments that arise here: t = (argument of the function) x
+// (relative step), with NL2SOL's relative step 1.5e-8, so |t| ~ 1e-8 ... 1e-7 for arguments of
+// order 1 ... 10.  Two terms, t + t^2/2, have relative truncation error t^2/6: 2e-17 at
+// |t| = 1e-8 -- below FP64 rounding -- and still 2e-11 at |t| = 1e-5.  For comparison, the
+// quantity being reproduced, the reference's computed numerator r(x+h) - r(x), carries a
+// rounding noise of 1e-16/|t| (1e-8 ... 1e-11 over the same range) and differs from the
+// derivative it stands for by t/2.  -DFMC_PERT_TERMS=4 keeps two more terms (error t^4/120);
+// it costs 2 FMAs per transcendental and row (measured on C2: 3.7 % of the step) and changes
+// the C2 ensemble mean by 4e-12 relative (profiles/r1_pert_terms.json).
+#ifndef FMC_PERT_TERMS
+#define FMC_PERT_TERMS 2
+#endif
 FMC_HD FMC_INLINE double expm1_small(double t) {
+#if FMC_PERT_TERMS == 2
+  return fma(0.5 * t, t, t);
+#else
   return fma(t * t, fma(t, fma(t, 1.0 / 24.0, 1.0 / 6.0), 0.5), t);
+#endif
 }
 FMC_HD FMC_INLINE double log1p_small(double u) {
+#if FMC_PERT_TERMS == 2
+  return fma(-0.5 * u, u, u);
+#else
   return fma(u * u, fma(u, fma(u, -0.25, 1.0 / 3.0), -0.5), u);
+#endif
 }
 
 FMC_HD FMC_INLINE Pert exp(const Pert& a) {

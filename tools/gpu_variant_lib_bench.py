@@ -15,7 +15,7 @@ import fitter_mc_b200.api as api
 api.lib_path = lambda: %(lib)r
 import fitter_mc_b200 as fmc, datasets, oracle_lib as oracle
 out = {}
-for name in ("c2", "c2p3", "c1"):
+for name in ("c2",):
     model, x, y, err = datasets.dataset(name)
     start, _ = oracle.fit_data(model, x, y, err, fmc.initialise_model(model)["params_init"])
     ctx = fmc.Context(0); ctx.set_data(model, x, y, err)
