@@ -287,6 +287,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resamples_per_gpu_per_step": nres, "seed": SEED,
+                       "jacobian": "forward differences (nl2sno, the reference's path)",
                        "l2": "flushed between steps (256 MiB memset); working set (32 KB) lives in shared memory",
                        "geometry": ctx.geometry(), "per_fit": {"nfcall": F, "ngcall": G, "niter": tot[2], "passes": tot[3]},
                        "wall_s_timed_region": t_wall, "solver_safety_cap_hits_last_step": int(n_anomalies)},
