@@ -15,6 +15,23 @@
 #include "../../fitter_mc_b200/csrc/rng.cuh"
 #include "mgh_models.hpp"
 
+namespace fmc {
+// Exercises every operation pert.cuh / dual.cuh define (the bundled models use only + - * / exp pow).
+struct ModelAllOps {
+  static constexpr int NPARAM = 3;
+  static constexpr int NPROP = 1;
+  template <class T>
+  static T model_y(const T* p, double x) {
+    const T a = sqrt(p[0] * x + 1.0) * sin(p[1] * x) - cos(p[2]) / (1.0 + p[0] * p[0]);
+    const T b = log(p[1] + x) * pow(p[2], p[0]) + pow(x + 1.0, p[1]) - pow(p[0] + 2.0, 1.5);
+    const T c = (-p[2] + 3.0 * x) / (x + p[1]) + 2.0 / p[0] - (+p[1]) + (0.5 - p[2]) * (x - p[0]) + exp(-p[0] * x);
+    return a + b * 0.25 + c;
+  }
+  static void derived_properties(const double* p, double* q) { q[0] = p[0]; }
+};
+
+}  // namespace fmc
+
 using namespace fmc;
 
 namespace {
@@ -240,6 +257,7 @@ int emul_row_grad(int model, const double* x, double xi, double* grad) {
     case 2: row_grad<ModelPeaks10>(x, xi, grad); return 0;
     case 3: row_grad<ModelStiff4>(x, xi, grad); return 0;
     case 100: row_grad<ModelHandGrad>(x, xi, grad); return 0;
+    case 101: row_grad<ModelAllOps>(x, xi, grad); return 0;
   }
   return -1;
 }
@@ -281,6 +299,7 @@ int emul_row_model(int model, const double* x, const double* h, double xi, doubl
     case 1: row_model_both<ModelTest4>(x, h, xi, m0, dm_engine, dm_plain); return 0;
     case 2: row_model_both<ModelPeaks10>(x, h, xi, m0, dm_engine, dm_plain); return 0;
     case 3: row_model_both<ModelStiff4>(x, h, xi, m0, dm_engine, dm_plain); return 0;
+    case 101: row_model_both<ModelAllOps>(x, h, xi, m0, dm_engine, dm_plain); return 0;
   }
   return -1;
 }

@@ -136,3 +136,45 @@ def test_emulated_product_solver_matches_oracle_per_fit(emul, oracle, name, nres
     assert same_first_call > 0.7, same_first_call
     # a pass over the data is needed only for the start of each call and for each trial point
     assert (co[:, :, 4] == co[:, :, 1]).mean() > 0.99
+
+
+def _mp_all_ops(mp, p, x):
+    x = mp.mpf(float(x))
+    a = mp.sqrt(p[0] * x + 1) * mp.sin(p[1] * x) - mp.cos(p[2]) / (1 + p[0] * p[0])
+    b = mp.log(p[1] + x) * p[2] ** p[0] + (x + 1) ** p[1] - (p[0] + 2) ** mp.mpf(1.5)
+    c = (-p[2] + 3 * x) / (x + p[1]) + 2 / p[0] - p[1] + (mp.mpf(0.5) - p[2]) * (x - p[0]) + mp.exp(-p[0] * x)
+    return a + b / 4 + c
+
+
+def test_every_operation_of_pert_and_dual_against_multiprecision(emul):
+    """A plug-in may use + - * / exp log sqrt sin cos pow in any combination (pert.cuh, dual.cuh); the
+    bundled models use only some of them.  A test model that uses all of them: the perturbation
+    result equals m(x) - m(x + h e_k) and the dual-number result equals dm/dp_k, both computed with
+    80 digits."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 80
+    emul.emul_row_grad.argtypes = [C.c_int, _dp, C.c_double, _dp]
+    rng = np.random.default_rng(101)
+    worst_pert, worst_dual, worst_plain = 0.0, 0.0, 0.0
+    for _ in range(200):
+        x = np.array([rng.uniform(0.3, 3.0), rng.uniform(0.3, 3.0), rng.uniform(0.3, 3.0)])
+        h = 1.4901161193847656e-08 * np.maximum(np.abs(x), 1.0 / rng.uniform(0.5, 50, size=3))
+        xi = float(rng.uniform(0.1, 4.0))
+        m0, de, dpl, gr = C.c_double(), np.zeros(3), np.zeros(3), np.zeros(3)
+        assert emul.emul_row_model(101, _d(x), _d(h), xi, C.byref(m0), _d(de), _d(dpl)) == 0
+        assert emul.emul_row_grad(101, _d(x), xi, _d(gr)) == 0
+        pm = [mp.mpf(float(v)) for v in x]
+        base = _mp_all_ops(mp, pm, xi)
+        assert abs(mp.mpf(m0.value) - base) <= 2e-15 * max(abs(base), 1)
+        for k in range(3):
+            ps = list(pm)
+            ps[k] = pm[k] + mp.mpf(float(h[k]))                    # the exact step, as pert.cuh carries it
+            exact = base - _mp_all_ops(mp, ps, xi)
+            worst_pert = max(worst_pert, float(abs(mp.mpf(float(de[k])) - exact) / abs(exact)))
+            worst_plain = max(worst_plain, float(abs(mp.mpf(float(dpl[k])) - exact) / abs(exact)))
+            deriv = mp.diff(lambda t, k=k: _mp_all_ops(mp, [t if i == k else pm[i] for i in range(3)], xi), pm[k])
+            worst_dual = max(worst_dual, float(abs(mp.mpf(float(gr[k])) - deriv) / abs(deriv)))
+    print("\n[all ops] worst rel. error: perturbation %.2e (plain double differences %.2e), dual numbers %.2e"
+          % (worst_pert, worst_plain, worst_dual))
+    assert worst_pert < 5e-13 and worst_dual < 5e-13                # cancellation between the terms of the model
+    assert worst_plain > 1e3 * worst_pert                           # what the engine avoids
