@@ -78,6 +78,7 @@ def lib():
     L.fmc_bootstrap_run_binned.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, C.c_ulonglong,
                                            C.c_longlong, C.c_int, _dp, _dp, _dp, _dp, _lp, _lp, C.c_int, _dp, _dp,
                                            C.c_void_p]
+    L.fmc_set_fit_mapping.argtypes = [C.c_void_p, C.c_int]
     L.fmc_set_jacobian_mode.argtypes = [C.c_void_p, C.c_int]
     L.fmc_model_has_analytic_jacobian.argtypes = [C.c_int]
     L.fmc_set_histogram.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -339,6 +340,12 @@ class Context:
         README:35-42): exact Jacobian rows from the plug-in's model_grad or by dual numbers."""
         code = {"forward-difference": 0, "fd": 0, 0: 0, "analytic": 1, 1: 1}[mode]
         _check(lib().fmc_set_jacobian_mode(self._h, code), "fmc_set_jacobian_mode")
+
+    def set_fit_mapping(self, mapping):
+        """"thread" (default: one resample per thread) or "warp" (one resample per warp; experimental,
+        meant for large ndata x nparam -- csrc/warp_kernel.cuh)."""
+        code = {"thread": 0, 0: 0, "warp": 1, 1: 1}[mapping]
+        _check(lib().fmc_set_fit_mapping(self._h, code), "fmc_set_fit_mapping")
 
     def set_histogram(self, nbins, lo=None, hi=None):
         """Bin every fitted parameter and property on the device (replaces histogram_<prop>.dat,

@@ -11,6 +11,7 @@
 
 #include "../../include/fmc_b200.h"
 #include "model_registry.cuh"
+#include "warp_kernel.cuh"
 
 // (no `using namespace fmc` here: fmc::exp & co. must not leak into the global scope, where
 // they would collide with the CUDA math headers)
@@ -30,6 +31,7 @@ namespace {
 
 thread_local std::string g_last_cuda_error;
 int g_default_jac = 0;  // Jacobian mode of the one-call entry points (fmc_set_jacobian_mode(NULL, .))
+int g_default_mapping = 0;  // fit mapping of the one-call entry points (fmc_set_fit_mapping(NULL, .))
 
 #define FMC_CUDA(call)                                                                   \
   do {                                                                                   \
@@ -153,6 +155,7 @@ struct fmc_context {
   long long hist_own_cap = 0;
   int hist_bins = 0;
   int jac = fmc::JAC_FD;  // how Jacobian rows are formed (fmc_set_jacobian_mode)
+  int mapping = 0;        // 0 = one fit per thread, 1 = one fit per warp (fmc_set_fit_mapping)
   double hist_lo[fmc::HIST_MAX_QUANT] = {0};
   double hist_scale[fmc::HIST_MAX_QUANT] = {0};
   long long rowj_cap = 0;
@@ -334,6 +337,15 @@ int fmc_set_jacobian_mode(fmc_context* c, int mode) {
     c->jac = mode;
   else
     g_default_jac = mode;  // the one-call entry points
+  return FMC_OK;
+}
+
+int fmc_set_fit_mapping(fmc_context* c, int mapping) {
+  if (mapping != FMC_FIT_PER_THREAD && mapping != FMC_FIT_PER_WARP) return FMC_ERR_BAD_ARG;
+  if (c)
+    c->mapping = mapping;
+  else
+    g_default_mapping = mapping;  // the one-call entry points
   return FMC_OK;
 }
 
@@ -546,20 +558,28 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   int bps = 0;
   const int jac = c->jac;
   if (jac == fmc::JAC_ANALYTIC && !m.analytic) return FMC_ERR_BAD_ARG;  // double-only model_y, no model_grad
-  FMC_CUDA(m.occupancy(inject, smem, jac, shmem, &bps));
+  const bool per_warp = c->mapping == FMC_FIT_PER_WARP;
+  const fmc::WarpEntry wentry = per_warp ? fmc::fmc_warp_entry(c->model) : fmc::WarpEntry{nullptr, nullptr};
+  if (per_warp) {
+    if (!wentry.launch) return FMC_ERR_BAD_MODEL;
+    FMC_CUDA(wentry.occupancy(inject, smem, jac, shmem, &bps));
+  } else {
+    FMC_CUDA(m.occupancy(inject, smem, jac, shmem, &bps));
+  }
   if (bps < 1) {
     g_last_cuda_error = "kernel does not fit on an SM";
     return FMC_ERR_CUDA;
   }
   // persistent grid for the refill kernels: every SM full, threads take fits from a counter
   const long long full_grid = (long long)c->num_sms * bps;
-  c->geom[1] = FMC_THREADS;
+  c->geom[1] = per_warp ? FMC_WARP_THREADS : FMC_THREADS;
   c->geom[2] = bps;
   c->geom[3] = c->num_sms;
 
   // first nl2sno call: shared Jacobian at params_start when its rows fit in shared memory too
   const size_t shmem_shared = (sizeof(RowData) + sizeof(double) * (1 + P)) * (size_t)c->n_pad;
-  const bool shared_init = jac == fmc::JAC_FD && shmem_shared + 1024 <= (size_t)c->max_smem_optin;
+  const bool shared_init =
+      !per_warp && jac == fmc::JAC_FD && shmem_shared + 1024 <= (size_t)c->max_smem_optin;
   double* g0_dev = nullptr;
   if (shared_init) {
     const long long need = (long long)(1 + P) * c->n_pad + PP;
@@ -593,8 +613,21 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     const long long need = (cnt + FMC_THREADS - 1) / FMC_THREADS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if (per_warp) {  // one warp per fit: both nl2sno calls inside one kernel (warp_kernel.cuh)
+      const long long warps_per_block = FMC_WARP_THREADS / 32;
+      long long wgrid = full_grid;
+      const long long wneed = (cnt + warps_per_block - 1) / warps_per_block;
+      if (wgrid > wneed) wgrid = wneed;
+      if (wgrid < 1) wgrid = 1;
+      grid = wgrid;
+    }
     c->geom[0] = (int)grid;
-    for (int call = 0; call < 2; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
+    if (per_warp) {
+      a.call = 0;
+      a.next_id = c->counters_dev + 2 * ch;
+      FMC_CUDA(wentry.launch(a, inject, smem, jac, (int)grid, shmem, c->stream));
+    }
+    for (int call = 0; call < 2 && !per_warp; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
       a.call = call;
       a.next_id = c->counters_dev + 2 * ch + call;
       if (call == 0 && shared_init)
@@ -785,6 +818,7 @@ int bootstrap_run_impl(int model, int ndata, const double* x, const double* y, c
       }
       fmc_set_accumulator_dev(c, nullptr);
       c->jac = g_default_jac;
+      c->mapping = g_default_mapping;
       fmc_set_histogram_dev(c, nullptr);
       if ((rc = fmc_set_histogram(c, nbins, bin_lo, bin_hi)) != FMC_OK) break;  // cached context: also switches off
       if ((rc = fmc_launch(c, params_start, cnt, seed, first_counter + lo, zdev, keep ? 1 : 0)) != FMC_OK) break;
@@ -865,6 +899,7 @@ int fmc_fit_once(int model, int ndata, const double* x, const double* y, const d
   fmc_set_accumulator_dev(c, nullptr);
   fmc_set_histogram(c, 0, nullptr, nullptr);  // the cached context may have binned before
   c->jac = g_default_jac;
+  c->mapping = g_default_mapping;
   rc = fmc_launch(c, params, 1, 0ULL, 0, zdev, 1);
   const int P = models()[model].nparam;
   std::vector<double> pout(P);

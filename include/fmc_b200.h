@@ -144,6 +144,17 @@ int fmc_last_anomalies(fmc_context* ctx, long long* ids, int* flags, int cap);
 int fmc_set_jacobian_mode(fmc_context* ctx, int mode);
 int fmc_model_has_analytic_jacobian(int model);
 
+/* ---- how fits are mapped onto the GPU ---------------------------------------------------
+ * FMC_FIT_PER_THREAD (default): one resample per thread, threads refill from a shared
+ * counter; the measured choice for the small fits of this path.
+ * FMC_FIT_PER_WARP: one resample per warp -- the data points of a pass are split over the 32
+ * lanes and the p x p sums combined by warp shuffles; meant for large ndata x nparam.
+ * EXPERIMENTAL: same results up to summation order; not yet measured on a GPU (round 1).
+ * ctx = NULL sets the mapping of the one-call entry points. */
+#define FMC_FIT_PER_THREAD 0
+#define FMC_FIT_PER_WARP 1
+int fmc_set_fit_mapping(fmc_context* ctx, int mapping);
+
 /* ---- binned distributions -------------------------------------------
  * Replaces the reference's histogram_<prop>.dat dumps -- one list-directed text line per
  * resample and property, written inside an OMP CRITICAL (bootstrap.f90:301-308, 319-325,

@@ -120,6 +120,119 @@ int bootstrap(int n, const double* x, const double* y, const double* err, const 
 }
 
 
+// ---- host image of the warp-per-fit mapping (csrc/warp_kernel.cuh): the rows of a pass are
+// dealt to 32 "lanes" in groups of four (lane l: groups l, l+32, ...), each lane accumulates
+// its own partial sums, and a butterfly (the order of __shfl_xor with offsets 16, 8, 4, 2, 1)
+// combines them.  Returns the totals as lane 0 sees them and checks that all lanes agree.
+template <int P>
+bool butterfly(PassAcc<P>* lane_acc, bool with_b) {
+  constexpr int PP = P * (P + 1) / 2;
+  constexpr int NV = 1 + P + PP + P;
+  double v[32][NV];
+  for (int l = 0; l < 32; ++l) {
+    int m = 0;
+    v[l][m++] = lane_acc[l].f;
+    for (int i = 0; i < P; ++i) v[l][m++] = lane_acc[l].g[i];
+    for (int i = 0; i < PP; ++i) v[l][m++] = lane_acc[l].G[i];
+    for (int i = 0; i < P; ++i) v[l][m++] = with_b ? lane_acc[l].lky[i] : 0.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    double nv[32][NV];
+    for (int l = 0; l < 32; ++l)
+      for (int m = 0; m < NV; ++m) nv[l][m] = v[l][m] + v[l ^ o][m];
+    std::memcpy(v, nv, sizeof(v));
+  }
+  bool same = true;
+  for (int l = 1; l < 32; ++l) same = same && std::memcmp(v[l], v[0], sizeof(v[0])) == 0;
+  int m = 0;
+  lane_acc[0].f = v[0][m++];
+  for (int i = 0; i < P; ++i) lane_acc[0].g[i] = v[0][m++];
+  for (int i = 0; i < PP; ++i) lane_acc[0].G[i] = v[0][m++];
+  for (int i = 0; i < P; ++i) lane_acc[0].lky[i] = v[0][m++];
+  return same;
+}
+
+template <class M, int JAC>
+bool warp_pass(Nl2<M::NPARAM>& s, bool first, int n, const double* x, const double* yfit, const double* rerr) {
+  constexpr int P = M::NPARAM;
+  const int n_pad = (n + 3) / 4 * 4;
+  PassPoint<P> a, b;
+  double h1[P];
+  for (int i = 0; i < P; ++i) h1[i] = (first && JAC == JAC_ANALYTIC) ? 1.0 : s.hA[i];
+  a.set(s.x, first ? h1 : s.hA);
+  b.set(s.x0, s.hJ);
+  PassAcc<P> lane_acc[32];
+  for (int l = 0; l < 32; ++l) {
+    lane_acc[l].zero();
+    for (int i = 4 * l; i < n_pad; i += 4 * 32)
+      for (int m = 0; m < 4; ++m) {
+        const int r = i + m;
+        if (r >= n) continue;  // padding rows contribute exactly zero on the device (rerr = 0)
+        if (!first)
+          row_accumulate<M, true, JAC>(a, b, x[r], yfit[r], rerr[r], lane_acc[l]);
+        else
+          row_accumulate<M, false, JAC>(a, a, x[r], yfit[r], rerr[r], lane_acc[l]);
+      }
+  }
+  const bool same = butterfly<P>(lane_acc, !first);
+  if constexpr (JAC == JAC_ANALYTIC)
+    pass_finish_analytic<P>(lane_acc[0], s);
+  else
+    pass_finish<P>(lane_acc[0], s);
+  return same;
+}
+
+// one fit_data through the warp mapping; returns false if the lanes ever disagreed
+template <class M, int JAC>
+bool fit_one_warp(int n, const double* x, const double* yfit, const double* err, double* params, int* counters) {
+  constexpr int P = M::NPARAM;
+  std::vector<double> rerr(n);
+  for (int i = 0; i < n; ++i) rerr[i] = 1.0 / err[i];
+  Nl2<P> s;
+  std::memset(&s, 0, sizeof(s));
+  s.reset_fit();
+  bool same = true;
+  for (int call = 0; call < 2; ++call) {
+    s.begin(params);
+    int passes = 0;
+    same = warp_pass<M, JAC>(s, true, n, x, yfit, rerr.data()) && same;
+    ++passes;
+    bool more = s.resume();
+    while (more) {
+      same = warp_pass<M, JAC>(s, false, n, x, yfit, rerr.data()) && same;
+      ++passes;
+      more = s.resume();
+      if (more && passes > 2 * (k::mxfcal + k::mxiter)) more = false;
+    }
+    for (int i = 0; i < P; ++i) params[i] = s.x[i];
+    if (counters) {
+      int* c = counters + 5 * call;
+      c[0] = s.rc;
+      c[1] = s.nfcall;
+      c[2] = s.ngcall;
+      c[3] = s.niter;
+      c[4] = passes;
+    }
+  }
+  return same;
+}
+
+template <class M, int JAC>
+int bootstrap_warp(int n, const double* x, const double* y, const double* err, const double* start, long long nres,
+                   const double* z, double* params_out, int* counters_out) {
+  constexpr int P = M::NPARAM;
+  std::vector<double> yfit(n), p(P);
+  int disagreements = 0;
+  for (long long r = 0; r < nres; ++r) {
+    for (int i = 0; i < n; ++i) yfit[i] = fma(z[(size_t)r * n + i], err[i], y[i]);
+    for (int i = 0; i < P; ++i) p[i] = start[i];
+    if (!fit_one_warp<M, JAC>(n, x, yfit.data(), err, p.data(), counters_out ? counters_out + 10 * r : nullptr))
+      ++disagreements;
+    std::memcpy(params_out + (size_t)r * P, p.data(), sizeof(double) * P);
+  }
+  return disagreements;
+}
+
 // model value and forward differences dm[k] = m(x) - m(x + h_k e_k) through (a) the product's
 // row_model (perturbation arithmetic for generic plug-ins) and (b) p+1 plain evaluations
 template <class M>
@@ -248,6 +361,25 @@ int emul_gqtstp2(const double* hmat, const double* dig, const double* d, double 
   *ka_out = s.kagqt;
   *anomaly_out = s.anomaly;
   return 0;
+}
+
+// The warp-per-fit mapping (host image).  Returns the number of fits in which the 32 lanes did
+// not end a butterfly with bitwise identical totals (must be 0), or -1 for a bad model id.
+int emul_bootstrap_warp(int model, int jac, int n, const double* x, const double* y, const double* err,
+                        const double* start, long long nres, const double* z, double* params_out,
+                        int* counters_out) {
+#define WARP_CASE(ID, M)                                                                                  \
+  case ID:                                                                                                \
+    return jac ? bootstrap_warp<M, JAC_ANALYTIC>(n, x, y, err, start, nres, z, params_out, counters_out)  \
+               : bootstrap_warp<M, JAC_FD>(n, x, y, err, start, nres, z, params_out, counters_out);
+  switch (model) {
+    WARP_CASE(0, ModelUser)
+    WARP_CASE(1, ModelTest4)
+    WARP_CASE(2, ModelPeaks10)
+    WARP_CASE(3, ModelStiff4)
+  }
+#undef WARP_CASE
+  return -1;
 }
 
 int emul_row_grad(int model, const double* x, double xi, double* grad) {
