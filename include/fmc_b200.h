@@ -19,7 +19,11 @@
  *    every fit; so does this library (the codes are returned as a histogram instead).
  *  - there is no CPU fallback: every compute entry point fails with FMC_ERR_NO_DEVICE
  *    when no CUDA device is usable.
- *  - not re-entrant per context; use one context per host thread / per GPU.
+ *  - not re-entrant per context; use one context per host thread / per GPU.  The one-call
+ *    entry points (fmc_bootstrap_run, fmc_bootstrap_run_binned, fmc_fit_once,
+ *    fmc_generate_offsets) share one cached context per GPU and are to be called from one
+ *    host thread at a time -- like the routine they replace, which the reference calls once,
+ *    outside any parallel region (fitter_mc.f90:36).
  *  - results are a deterministic function of (data, params_start, seed, global resample id):
  *    every resample draws its Gaussian offsets from a counter-based generator keyed by its
  *    global id, so any split of [first_counter, first_counter+nresample) over launches,
