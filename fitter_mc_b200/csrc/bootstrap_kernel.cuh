@@ -75,6 +75,9 @@ struct KernelArgs {
   unsigned long long* next_id;  // work counter of this launch, zeroed beforehand
   unsigned long long* anom;     // anomaly log (fits that hit a safety cap), zeroed per launch
   double* acc;              // accumulator block, zeroed before the first chunk
+  // experimental (trial1_kernel.cuh): results of the first trial pass of call 0, computed by a
+  // uniform kernel; [flag, f, g(P), G(PP), lky(P)][cap].  nullptr = not used.
+  const double* trial1;
 };
 
 // Optional binned distributions of the fitted parameters and properties (replaces the
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(FMC_THREADS) init_shared_kernel(const KernelAr
 // that finishes takes the next fit from a shared counter, so lanes of a warp are at different
 // iterations of different fits but always execute the same thing next -- one trial pass
 // (residual + speculative Jacobian at x, Jacobian at x0 for the secant update).
-template <class M, bool INJECT, bool SMEM, int JAC = JAC_FD>
+template <class M, bool INJECT, bool SMEM, int JAC = JAC_FD, bool TRIAL1 = false>
 __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int Q = M::NPROP;
@@ -397,7 +400,26 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
       for (int i = 0; i < PP; ++i) s.res_G[i] = a.init[(1 + P + i) * a.cap + slot];
       fit_passes = 1;
       active = true;
-      if (s.resume()) return;
+      if (s.resume()) {
+        if constexpr (TRIAL1) {
+          // The solver has just re-derived the first trial point from the initial sums, exactly as
+          // trial1_kernel did; that kernel already made the pass at it, so take its sums instead.
+          if (a.call == 0 && a.trial1[slot] != 0.0) {
+            s.res_f = a.trial1[a.cap + slot];
+#pragma unroll
+            for (int i = 0; i < P; ++i) s.res_g[i] = a.trial1[(2 + i) * a.cap + slot];
+#pragma unroll
+            for (int i = 0; i < PP; ++i) s.res_G[i] = a.trial1[(2 + P + i) * a.cap + slot];
+#pragma unroll
+            for (int i = 0; i < P; ++i) s.res_lky[i] = a.trial1[(2 + P + PP + i) * a.cap + slot];
+            fit_passes = 2;
+            if (s.resume()) return;
+            finish_call();
+            continue;
+          }
+        }
+        return;
+      }
       finish_call();  // ended without a single trial step (e.g. residual too big at the start)
     }
   };
