@@ -112,3 +112,25 @@ def test_product_does_not_touch_the_oracle():
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "oracle_lib" not in text and "fmc_oracle" not in text and "oracle/" not in text, \
                         os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_a_c_program_links(fmc, tmp_path):
+    """The boundary is a C ABI: include/fmc_b200.h must compile as C99 (no C++, no torch types) and a
+    C program must link against libfmc_b200.so and call the host-side entry points."""
+    import subprocess
+
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include "fmc_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '  int np = 0, nq = 0; double init[FMC_MAX_PARAM]; char pn[FMC_MAX_PARAM][3], qn[FMC_MAX_PARAM][3], name[32];\n'
+                   '  if (fmc_initialise_model(0, &np, &nq, init, pn, qn, name) != FMC_OK) return 1;\n'
+                   '  printf("%s %d %d %.1f %s\\n", name, np, nq, fmc_model_y(0, init, 0.0), fmc_strerror(FMC_ERR_NO_DEVICE));\n'
+                   '  return fmc_model_count() < 1;\n}\n')
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(fmc.lib_path())
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                           "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir, "-lfmc_b200",
+                           "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0
+    assert out.stdout.startswith("test 3 1 2.0 no usable CUDA device")
