@@ -13,6 +13,7 @@
 // identical data (tests/test_oracle_solver.py), (iii) the mcfit.py probe
 // numbers in BASELINE.md and golden vectors generated from mcfit.py
 // (tests/golden), (iv) the published minima of ten classical test problems
+// and the NIST StRD certified values of Misra1a, DanWood and BoxBOD
 // (tests/test_classic_problems.py).  The RANLUX part IS pinned by ranlux.f:399-473.
 //
 // Layout convention: the reference's 1-based IV()/V() maps (SURVEY.md

@@ -442,6 +442,8 @@ int emul_fit_classic(int problem, int jac, int n, const double* t, const double*
     MGH_CASE(7, MghBox3D)
     MGH_CASE(8, MghBrownDennis)
     MGH_CASE(9, MghJennrichSampson)
+    MGH_CASE(10, NistSaturation)
+    MGH_CASE(11, NistDanWood)
   }
 #undef MGH_CASE
   return -1;

@@ -121,6 +121,24 @@ struct MghJennrichSampson {
   }
 };
 
+// NIST StRD Misra1a and BoxBOD: y_i - b1 (1 - exp(-b2 x_i)).
+struct NistSaturation {
+  MGH_COMMON(2)
+  template <class T>
+  static T model_y(const T* p, double t) {
+    return p[0] * (1.0 - exp(-p[1] * t));
+  }
+};
+
+// NIST StRD DanWood: y_i - b1 x_i^b2.
+struct NistDanWood {
+  MGH_COMMON(2)
+  template <class T>
+  static T model_y(const T* p, double t) {
+    return p[0] * pow(t, p[1]);
+  }
+};
+
 #undef MGH_COMMON
 
 }  // namespace fmc

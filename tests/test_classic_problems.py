@@ -84,7 +84,27 @@ def _problems():
     return P
 
 
+def _nist():
+    """NIST StRD nonlinear regression problems: name -> (emul id, x, y, residual, starts, certified
+    parameters, certified residual sum of squares)."""
+    N = {}
+    mx = np.array([77.6, 114.9, 141.1, 190.8, 239.9, 289.0, 332.8, 378.4, 434.8, 477.3, 536.8, 593.1, 689.1, 760.0])
+    my = np.array([10.07, 14.73, 17.94, 23.93, 29.61, 35.18, 40.02, 44.82, 50.76, 55.05, 61.01, 66.40, 75.47, 81.78])
+    N["misra1a"] = (10, mx, my, lambda p: my - p[0] * (1 - np.exp(-p[1] * mx)), [[500.0, 1e-4], [250.0, 5e-4]],
+                    [2.3894212918e02, 5.5015643181e-04], 1.2455138894e-01)
+    dx = np.array([1.309, 1.471, 1.490, 1.565, 1.611, 1.680])
+    dy = np.array([2.138, 3.421, 3.597, 4.340, 4.882, 5.660])
+    N["danwood"] = (11, dx, dy, lambda p: dy - p[0] * dx ** p[1], [[1.0, 5.0], [0.7, 4.0]],
+                    [7.6886226176e-01, 3.8604055871e00], 4.3173084083e-03)
+    bx = np.array([1.0, 2.0, 3.0, 5.0, 7.0, 10.0])
+    by = np.array([109.0, 149.0, 149.0, 191.0, 213.0, 224.0])
+    N["boxbod"] = (10, bx, by, lambda p: by - p[0] * (1 - np.exp(-p[1] * bx)), [[100.0, 0.75]],
+                   [2.1380940889e02, 5.4723748542e-01], 1.1680088766e03)
+    return N
+
+
 PROBLEMS = _problems()
+NIST = _nist()
 # Minima at which the Jacobian is rank deficient (equal columns for Jennrich & Sampson, the
 # singular local minimum of Freudenstein & Roth, Powell's singular function).  A solver call
 # restarted AT such a point factors a matrix whose trailing pivot is pure rounding noise: the
@@ -180,3 +200,19 @@ def test_product_solver_agrees_with_oracle_on_classic_problems(emul, oracle, nam
     if jac == 0 and name not in ("powell_singular",):
         # same algorithm: the first call takes (almost) the same number of iterations
         assert abs(int(cnt[0, 3]) - int(ocnt[0, 3])) <= 2, (cnt, ocnt)
+
+
+@pytest.mark.parametrize("name", sorted(NIST))
+def test_nist_strd_certified_values(emul, oracle, name):
+    """NIST Statistical Reference Datasets (nonlinear regression): certified parameter values (11
+    digits, computed by NIST in 500-digit arithmetic) and residual sums of squares, reproduced by the
+    oracle's nl2sno and by the product's solver, in both Jacobian modes."""
+    pid, x, y, resid, starts, cert, rss = NIST[name]
+    for start in starts:
+        got, cnt, ss = _oracle_fit(oracle, resid, len(x), start)
+        print("\n[nist/oracle %s from %s] %s rc %s sumsq %.11g" % (name, start, got, cnt[:, 0].tolist(), ss))
+        assert np.allclose(got, cert, rtol=2e-8) and np.isclose(ss, rss, rtol=1e-9)
+        for jac in (0, 1):
+            pg, pc, anomaly = _emul_fit(emul, pid, jac, x, y, start)
+            pss = float(np.sum(resid(pg) ** 2))
+            assert anomaly == 0 and np.allclose(pg, cert, rtol=2e-8) and np.isclose(pss, rss, rtol=1e-9), (jac, pg, pss)
