@@ -105,6 +105,14 @@ def _nist():
 
 PROBLEMS = _problems()
 NIST = _nist()
+# Three of the classical problems are also NIST StRD datasets of "higher difficulty" (MGH09, MGH10,
+# MGH17) with certified parameters and residual sums of squares.
+NIST_CERTIFIED = {
+    "kowalik_osborne": ([1.9280693458e-01, 1.9128232873e-01, 1.2305650693e-01, 1.3606233068e-01], 3.0750560385e-04),
+    "meyer": ([5.6096364710e-03, 6.1813463463e03, 3.4522363462e02], 8.7945855171e01),
+    "osborne1": ([3.7541005211e-01, 1.9358469127e00, -1.4646871366e00, 1.2867534640e-02, 2.2122699662e-02],
+                 5.4648946975e-05),
+}
 # Minima at which the Jacobian is rank deficient (equal columns for Jennrich & Sampson, the
 # singular local minimum of Freudenstein & Roth, Powell's singular function).  A solver call
 # restarted AT such a point factors a matrix whose trailing pivot is pure rounding noise: the
@@ -171,6 +179,10 @@ def test_oracle_nl2sno_finds_the_published_minimum(oracle, name):
         assert np.isclose(ss, fstar, rtol=2e-5)                  # the published 6-digit value
     if xstar is not None and name != "powell_singular":
         assert np.allclose(x, xstar, rtol=2e-4, atol=1e-6)
+    if name in NIST_CERTIFIED:
+        cert, rss = NIST_CERTIFIED[name]
+        assert np.isclose(ss, rss, rtol=1e-10)                   # certified to 11 digits
+        assert np.allclose(x, cert, rtol=2e-6)                   # ill-conditioned: limited by the f-tolerance
     if name == "powell_singular":                                # singular Jacobian: slow approach to 0
         assert np.abs(x).max() < 1e-3
     # a local minimiser by an independent code started at the answer does not move
@@ -197,6 +209,9 @@ def test_product_solver_agrees_with_oracle_on_classic_problems(emul, oracle, nam
         assert np.isclose(ss, oss, rtol=1e-9)                     # the same minimum ...
     if name != "powell_singular":
         assert np.allclose(got, want, rtol=2e-6, atol=1e-9)       # ... at the same point
+    if name in NIST_CERTIFIED:
+        cert, rss = NIST_CERTIFIED[name]
+        assert np.isclose(ss, rss, rtol=1e-10) and np.allclose(got, cert, rtol=2e-6)
     if jac == 0 and name not in ("powell_singular",):
         # same algorithm: the first call takes (almost) the same number of iterations
         assert abs(int(cnt[0, 3]) - int(ocnt[0, 3])) <= 2, (cnt, ocnt)
