@@ -444,6 +444,7 @@ int emul_fit_classic(int problem, int jac, int n, const double* t, const double*
     MGH_CASE(9, MghJennrichSampson)
     MGH_CASE(10, NistSaturation)
     MGH_CASE(11, NistDanWood)
+    MGH_CASE(12, NistLanczos)
   }
 #undef MGH_CASE
   return -1;

@@ -139,6 +139,15 @@ struct NistDanWood {
   }
 };
 
+// NIST StRD Lanczos3: y_i - (b1 exp(-b2 x) + b3 exp(-b4 x) + b5 exp(-b6 x)), six parameters.
+struct NistLanczos {
+  MGH_COMMON(6)
+  template <class T>
+  static T model_y(const T* p, double t) {
+    return p[0] * exp(-p[1] * t) + p[2] * exp(-p[3] * t) + p[4] * exp(-p[5] * t);
+  }
+};
+
 #undef MGH_COMMON
 
 }  // namespace fmc

@@ -100,8 +100,20 @@ def _nist():
     by = np.array([109.0, 149.0, 149.0, 191.0, 213.0, 224.0])
     N["boxbod"] = (10, bx, by, lambda p: by - p[0] * (1 - np.exp(-p[1] * bx)), [[100.0, 0.75]],
                    [2.1380940889e02, 5.4723748542e-01], 1.1680088766e03)
+    lx = 0.05 * np.arange(24.0)
+    ly = np.array([2.5134, 2.0443, 1.6684, 1.3664, 1.1232, 0.9269, 0.7679, 0.6389, 0.5338, 0.4479, 0.3776, 0.3197,
+                   0.2720, 0.2325, 0.1997, 0.1723, 0.1493, 0.1301, 0.1138, 0.1000, 0.0883, 0.0783, 0.0698, 0.0624])
+    N["lanczos3"] = (12, lx, ly,
+                     lambda p: ly - (p[0] * np.exp(-p[1] * lx) + p[2] * np.exp(-p[3] * lx) + p[4] * np.exp(-p[5] * lx)),
+                     [[1.2, 0.3, 5.6, 5.5, 6.5, 7.6], [0.5, 0.7, 3.6, 4.2, 4.0, 6.3]],
+                     [8.6816414977e-02, 9.5498101505e-01, 8.4400777463e-01, 2.9515951832e00, 1.5825685901e00,
+                      4.9863565084e00], 1.6117193594e-08)
     return N
 
+
+# parameters of a sum of three exponentials are ill-conditioned: the certified sum of squares is met
+# to 11 digits while the parameters are only determined to ~1e-6 at NL2SOL's default tolerances
+NIST_PARAM_RTOL = {"lanczos3": 1e-5}
 
 PROBLEMS = _problems()
 NIST = _nist()
@@ -226,8 +238,9 @@ def test_nist_strd_certified_values(emul, oracle, name):
     for start in starts:
         got, cnt, ss = _oracle_fit(oracle, resid, len(x), start)
         print("\n[nist/oracle %s from %s] %s rc %s sumsq %.11g" % (name, start, got, cnt[:, 0].tolist(), ss))
-        assert np.allclose(got, cert, rtol=2e-8) and np.isclose(ss, rss, rtol=1e-9)
+        ptol = NIST_PARAM_RTOL.get(name, 2e-8)
+        assert np.allclose(got, cert, rtol=ptol) and np.isclose(ss, rss, rtol=1e-9)
         for jac in (0, 1):
             pg, pc, anomaly = _emul_fit(emul, pid, jac, x, y, start)
             pss = float(np.sum(resid(pg) ** 2))
-            assert anomaly == 0 and np.allclose(pg, cert, rtol=2e-8) and np.isclose(pss, rss, rtol=1e-9), (jac, pg, pss)
+            assert anomaly == 0 and np.allclose(pg, cert, rtol=ptol) and np.isclose(pss, rss, rtol=1e-9), (jac, pg, pss)
