@@ -44,7 +44,7 @@ def lib():
     path = lib_path()
     if not os.path.exists(path):
         raise ImportError("libfmc_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "or `make -C fitter_mc_b200 -j5`); fitter_mc_b200 has no CPU fallback")
+                          "or `make -C fitter_mc_b200 -j7`); fitter_mc_b200 has no CPU fallback")
     L = C.CDLL(path)
     L.fmc_strerror.restype = C.c_char_p
     L.fmc_strerror.argtypes = [C.c_int]
