@@ -6,6 +6,9 @@
 //
 // Environment (extensions; defaults reproduce the reference): FMC_NRAND (nrand_points, default
 // 100000, bootstrap.f90:9), FMC_SEED (31415, utils.f90:7), FMC_NGPUS (1), FMC_MODEL (0),
+// FMC_JACOBIAN (analytic = what the reference's README:35-42 calls replacing nl2sno by nl2sol with a
+// madj: exact Jacobian rows, from the plug-in's model_grad or by dual numbers; default: forward
+// differences, the reference's path),
 // FMC_HISTOGRAM (1 = write histogram_<prop>.dat, bootstrap.f90:263), FMC_HISTOGRAM_BINS (> 0:
 // bin the properties on the GPU instead of dumping one text line per resample -- the form that
 // scales to 1e8 resamples; histogram_<prop>.dat then holds "bin centre, count" lines).
@@ -128,6 +131,12 @@ int main(int argc, char** argv) {
   std::printf(" Model used is: %s\n", m.name);
   std::printf(" Number of parameters: %d\n\n", m.nparam);
   if (ndata < m.nparam) errstop("MONTE_CARLO_FIT_DATA", "Fewer data points than parameters.");
+
+  if (std::getenv("FMC_JACOBIAN") && std::string(std::getenv("FMC_JACOBIAN")) == "analytic") {
+    if (!fmc_model_has_analytic_jacobian(m.id))
+      errstop("MONTE_CARLO_FIT_DATA", "This model has no derivative (model_y is not generic and there is no model_grad).");
+    fmc_set_jacobian_mode(nullptr, FMC_JACOBIAN_ANALYTIC);
+  }
 
   std::vector<double> params(m.init.begin(), m.init.begin() + m.nparam), props(m.nprop > 0 ? m.nprop : 1);
   std::printf(" Initial parameter set:\n");

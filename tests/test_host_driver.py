@@ -165,3 +165,19 @@ def test_fitter_mc_binned_histogram_mode(tmp_path):
     assert len(qs) == 5 and np.all(np.diff(qs) > 0)
     sd = float(mc[0][1])
     assert abs((qs[3] - qs[1]) / 2 - sd) < 0.05 * sd and abs(qs[2] - float(mc[0][0])) < 0.05 * sd
+
+
+@pytest.mark.gpu
+def test_fitter_mc_analytic_jacobian_switch(tmp_path, oracle):
+    """FMC_JACOBIAN=analytic: the README's "replace the call to nl2sno with a call to nl2sol"."""
+    subprocess.check_call(["make", "-C", PKG, "fitter_mc"], stdout=subprocess.DEVNULL)
+    x, y, err = datasets.c1_probe()
+    np.savetxt(tmp_path / "probe.dat", np.c_[x, y, err])
+    env = dict(os.environ, FMC_JACOBIAN="analytic", FMC_NRAND="20000", FMC_HISTOGRAM="0")
+    out = subprocess.run([os.path.join(PKG, "fitter_mc"), "probe.dat"], cwd=tmp_path, capture_output=True, text=True,
+                         timeout=120, env=env)
+    assert out.returncode == 0, out.stderr
+    nums = [float(v) for v in re.findall(r"Parameter \S+\s+=\s+([-0-9.E+]+)", out.stdout)]
+    want, _ = oracle.fit_data(0, x, y, err, [0.0, 2.0, 1.0], flags=oracle.LSVMIN_PER_FIT | oracle.ANALYTIC_JAC)
+    assert np.allclose(nums[3:6], want, rtol=1e-8)
+    assert "Histogram of" not in out.stdout and " Program finished." in out.stdout
