@@ -55,6 +55,7 @@ FMC_HD inline int acc_len(int p, int q) { return 2 * (p + q) + ACC_NTAIL; }
 
 struct KernelArgs {
   const RowData* rows;  // [n_pad], padded rows have rerr = err = 0
+  const double* aux;    // [n_pad][NAUX] per-row auxiliary values of the model (pass_eval.cuh), or nullptr
   int n;                // data points
   int n_pad;            // multiple of 4
   double start[16];     // params_start: first guess of every fit and shift of the moment sums
@@ -113,8 +114,8 @@ FMC_INLINE __device__ void kahan_add(double& s, double& c, double v) {
 
 // One streaming pass of one fit over the n data points.
 template <class M, bool INJECT, bool WITH_B, int JAC = JAC_FD>
-FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, int n_pad,
-                                     unsigned long long seed, unsigned long long id,
+FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, const double* __restrict__ aux, int n,
+                                     int n_pad, unsigned long long seed, unsigned long long id,
                                      const double* __restrict__ zrow,
                                      const PassPoint<M::NPARAM>& pa, const PassPoint<M::NPARAM>& pb,
                                      PassAcc<M::NPARAM>& acc) {
@@ -131,18 +132,31 @@ FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, int n, in
       else
         zz = (double)z[m];
       const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
-      row_accumulate<M, WITH_B, JAC>(pa, pb, rd.x, yfit, rd.rerr, acc);
+      constexpr int NAUX = model_naux<M>::value;
+      const double* ra = NAUX > 0 ? aux + (i + m) * NAUX : nullptr;
+      if (NAUX > 0) __builtin_assume(ra != nullptr);
+      row_accumulate<M, WITH_B, JAC>(pa, pb, rd.x, yfit, rd.rerr, acc, ra);
     }
   }
 }
 
-template <bool SMEM>
-FMC_INLINE __device__ const RowData* stage_rows(const KernelArgs& a, unsigned char* smem_raw) {
-  if (!SMEM) return a.rows;
+// Rows (and, NAUX > 0, the per-row auxiliary values behind them) into shared memory.
+template <bool SMEM, int NAUX = 0>
+FMC_INLINE __device__ const RowData* stage_rows(const KernelArgs& a, unsigned char* smem_raw,
+                                                const double** aux_out = nullptr) {
+  if (!SMEM) {
+    if (aux_out) *aux_out = a.aux;
+    return a.rows;
+  }
   RowData* srows = reinterpret_cast<RowData*>(smem_raw);
   const double2* src = reinterpret_cast<const double2*>(a.rows);
   double2* dst = reinterpret_cast<double2*>(srows);
   for (int i = threadIdx.x; i < 2 * a.n_pad; i += blockDim.x) dst[i] = src[i];
+  if (NAUX > 0) {
+    double* saux = reinterpret_cast<double*>(smem_raw + sizeof(RowData) * a.n_pad);
+    for (int i = threadIdx.x; i < NAUX * a.n_pad; i += blockDim.x) saux[i] = a.aux[i];
+    if (aux_out) *aux_out = saux;
+  }
   __syncthreads();
   return srows;
 }
@@ -157,7 +171,8 @@ __global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs
   constexpr int P = M::NPARAM;
   constexpr int PP = P * (P + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const RowData* rows = stage_rows<SMEM>(a, smem_raw);
+  const double* aux = nullptr;
+  const RowData* rows = stage_rows<SMEM, model_naux<M>::value>(a, smem_raw, &aux);
   const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= a.nres) return;
   double x[P], h[P];
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs
   acc.zero();
   const unsigned long long id = (unsigned long long)(a.first + slot);
   const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
-  pass_loop<M, INJECT, false, JAC>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pa, acc);
+  pass_loop<M, INJECT, false, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pa, acc);
   double f, g[P], G[PP], lky[P];
   pass_scale<P>(acc, h, h, f, g, G, lky);
   a.init[slot] = f;
@@ -190,8 +205,13 @@ __global__ void __launch_bounds__(FMC_THREADS) init_pass_kernel(const KernelArgs
 // per fit and data point, only r = (y' - m0) w:  f += r^2,  g_k += (dm_k w) r  (8 FP64
 // operations instead of a model evaluation).
 //   rowJ[i][0] = m0_i,  rowJ[i][1+k] = dm_ik / err_i     (unscaled by 1/h_k)
+//   One-off O(n p) work: a single block of FMC_JAC0_THREADS threads (the bound keeps the launch
+//   valid whatever registers the plug-in's row_model needs).
+#define FMC_JAC0_THREADS 256
 template <class M>
-__global__ void jac0_kernel(const KernelArgs a, double* __restrict__ rowJ, double* __restrict__ G0) {
+__global__ void __launch_bounds__(FMC_JAC0_THREADS) jac0_kernel(const KernelArgs a, double* __restrict__ rowJ,
+                                                                double* __restrict__ G0) {
+  static_assert(M::NPARAM * (M::NPARAM + 1) / 2 <= FMC_JAC0_THREADS, "one thread per element of G0");
   constexpr int P = M::NPARAM;
   constexpr int PP = P * (P + 1) / 2;
   double x[P], h[P];
@@ -205,7 +225,8 @@ __global__ void jac0_kernel(const KernelArgs a, double* __restrict__ rowJ, doubl
   for (int i = threadIdx.x; i < a.n_pad; i += blockDim.x) {
     const RowData rd = a.rows[i];
     double m0, dm[P];
-    row_model<M>(pt, rd.x, m0, dm);
+    constexpr int NAUX = model_naux<M>::value;
+    row_model<M>(pt, rd.x, m0, dm, NAUX > 0 ? a.aux + i * NAUX : nullptr);
     rowJ[i * (1 + P)] = m0;
 #pragma unroll
     for (int kk = 0; kk < P; ++kk) rowJ[i * (1 + P) + 1 + kk] = dm[kk] * rd.rerr;
@@ -292,7 +313,8 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
   __shared__ double red[FMC_THREADS / 32];
   __shared__ unsigned int sh_rc[16];
   if (threadIdx.x < 16) sh_rc[threadIdx.x] = 0u;
-  const RowData* rows = stage_rows<SMEM>(a, smem_raw);
+  const double* aux = nullptr;
+  const RowData* rows = stage_rows<SMEM, model_naux<M>::value>(a, smem_raw, &aux);
   __syncthreads();
 
   Nl2<P> s;
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
       acc.zero();
       const unsigned long long id = (unsigned long long)(a.first + slot);
       const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
-      pass_loop<M, INJECT, true, JAC>(rows, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
+      pass_loop<M, INJECT, true, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
       if constexpr (JAC == JAC_ANALYTIC)
         pass_finish_analytic<P>(acc, s);
       else

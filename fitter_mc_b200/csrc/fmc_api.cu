@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -48,6 +49,22 @@ struct DevBuf {
   double* p = nullptr;
   ~DevBuf() {
     if (p) cudaFree(p);
+  }
+};
+
+// Make `device` current for the duration of an entry point and give the caller's device back
+// afterwards: the library is loaded into processes (torch, the Fortran driver's threads) that
+// have their own current device.
+struct DeviceGuard {
+  int prev = -1;
+  int dev;
+  cudaError_t err;
+  explicit DeviceGuard(int device) : dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
   }
 };
 
@@ -134,6 +151,13 @@ struct fmc_context {
   int model = -1, n = 0, n_pad = 0;
   RowData* rows_dev = nullptr;
   int rows_cap = 0;
+  // the same data once more in lane-major column order for the warp-per-fit kernel (warp_kernel.cuh)
+  double* cols_dev = nullptr;   // [4 + NAUX][n_w]: x, y, err, 1/err, the model's per-row auxiliary values
+  double* aux_dev = nullptr;    // [n_pad][NAUX]: the same auxiliary values in row order (thread-per-fit kernels)
+  int aux_cap = 0;
+  int cols_cap = 0, n_w = 0;
+  double* tscratch_dev = nullptr;  // [warps of the grid][n_w]: t_i = r_i / err_i between the two sweeps of a pass
+  long long tscratch_cap = 0;
   double* acc_own = nullptr;
   double* acc = nullptr;
   int acc_n = 0;
@@ -243,8 +267,11 @@ int fmc_create(fmc_context** out, int device) {
   const int ndev = device_count();
   if (ndev <= 0) return FMC_ERR_NO_DEVICE;
   if (device < 0 || device >= ndev) return FMC_ERR_BAD_ARG;
-  FMC_CUDA(cudaSetDevice(device));
-  fmc_context* c = new (std::nothrow) fmc_context();
+  DeviceGuard guard_(device);
+  FMC_CUDA(guard_.err);
+  // owned until every allocation below has succeeded: a failure frees what was created so far
+  std::unique_ptr<fmc_context, int (*)(fmc_context*)> owner(new (std::nothrow) fmc_context(), fmc_destroy);
+  fmc_context* c = owner.get();
   if (!c) return FMC_ERR_ALLOC;
   c->device = device;
   cudaDeviceProp prop;
@@ -264,15 +291,18 @@ int fmc_create(fmc_context** out, int device) {
   }
   FMC_CUDA(cudaMalloc(&c->anom_dev, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP)));
   FMC_CUDA(cudaMemset(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP)));
-  *out = c;
+  *out = owner.release();
   return FMC_OK;
 }
 
 int fmc_destroy(fmc_context* c) {
   if (!c) return FMC_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   if (c->inflight >= 0) cudaStreamSynchronize(c->stream);
   cudaFree(c->rows_dev);
+  cudaFree(c->cols_dev);
+  cudaFree(c->aux_dev);
+  cudaFree(c->tscratch_dev);
   cudaFree(c->acc_own);
   cudaFree(c->xbuf);
   cudaFree(c->initbuf);
@@ -306,7 +336,8 @@ int fmc_set_data(fmc_context* c, int model, int ndata, const double* x, const do
   if (ndata < m.nparam || ndata < 1) return FMC_ERR_BAD_ARG;
   for (int i = 0; i < ndata; ++i)
     if (!(err_y[i] > 0.0)) return FMC_ERR_BAD_ARG;  // bootstrap.f90:134-138
-  FMC_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
   const int n_pad = (ndata + 3) / 4 * 4;
   c->rows_host.resize(n_pad);
   for (int i = 0; i < n_pad; ++i) {
@@ -332,6 +363,44 @@ int fmc_set_data(fmc_context* c, int model, int ndata, const double* x, const do
   }
   FMC_CUDA(cudaMemcpyAsync(c->rows_dev, c->rows_host.data(), sizeof(RowData) * n_pad, cudaMemcpyHostToDevice,
                            c->stream));
+  // lane-major columns: element s = (4 j + m) 32 + l of a column is row 4 (32 j + l) + m, so that lane l
+  // of a warp owns the four-row groups l, l + 32, ... and every warp-wide load is contiguous
+  // per-row auxiliary values the model declares (functions of x_i alone, e.g. log x_i): once per data set
+  const int naux = m.naux;
+  std::vector<double> aux((size_t)(naux > 0 ? naux : 1) * n_pad, 0.0);
+  for (int i = 0; i < n_pad && naux > 0; ++i) m.row_aux(c->rows_host[i].x, &aux[(size_t)i * naux]);
+  if (naux > 0) {
+    if (naux * n_pad > c->aux_cap) {
+      cudaFree(c->aux_dev);
+      c->aux_dev = nullptr;
+      c->aux_cap = 0;
+      FMC_CUDA(cudaMalloc(&c->aux_dev, sizeof(double) * naux * n_pad));
+      c->aux_cap = naux * n_pad;
+    }
+    FMC_CUDA(cudaMemcpyAsync(c->aux_dev, aux.data(), sizeof(double) * naux * n_pad, cudaMemcpyHostToDevice, c->stream));
+  }
+  const int n_w = (ndata + 127) / 128 * 128;
+  const int ncol = 4 + naux;
+  std::vector<double> cols((size_t)ncol * n_w);
+  for (int sidx = 0; sidx < n_w; ++sidx) {
+    const int l = sidx & 31, jm = sidx >> 5, mm = jm & 3, j = jm >> 2;
+    const int row = 4 * (32 * j + l) + mm;
+    const bool real = row < ndata;
+    cols[sidx] = real ? x[row] : x[ndata - 1];
+    cols[(size_t)n_w + sidx] = real ? y[row] : 0.0;
+    cols[(size_t)2 * n_w + sidx] = real ? err_y[row] : 0.0;
+    cols[(size_t)3 * n_w + sidx] = real ? 1.0 / err_y[row] : 0.0;
+    for (int k = 0; k < naux; ++k) cols[(size_t)(4 + k) * n_w + sidx] = aux[(size_t)(real ? row : ndata - 1) * naux + k];
+  }
+  if (ncol * n_w > c->cols_cap) {
+    cudaFree(c->cols_dev);
+    c->cols_dev = nullptr;
+    c->cols_cap = 0;
+    FMC_CUDA(cudaMalloc(&c->cols_dev, sizeof(double) * ncol * n_w));
+    c->cols_cap = ncol * n_w;
+  }
+  FMC_CUDA(cudaMemcpyAsync(c->cols_dev, cols.data(), sizeof(double) * ncol * n_w, cudaMemcpyHostToDevice, c->stream));
+  c->n_w = n_w;
   FMC_CUDA(cudaStreamSynchronize(c->stream));
   if (model != c->model) c->hist_bins = 0;  // the binned quantities belong to a model
   c->model = model;
@@ -376,7 +445,8 @@ int fmc_set_histogram(fmc_context* c, int nbins, const double* lo, const double*
   if (nq > fmc::HIST_MAX_QUANT) return FMC_ERR_BAD_ARG;
   for (int j = 0; j < nq; ++j)
     if (!(hi[j] > lo[j]) || !std::isfinite(lo[j]) || !std::isfinite(hi[j])) return FMC_ERR_BAD_ARG;
-  FMC_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
   if (c->inflight >= 0) FMC_CUDA(cudaStreamSynchronize(c->stream));
   const long long need = (long long)nq * (nbins + 2);
   if (need > c->hist_own_cap) {
@@ -413,7 +483,8 @@ int fmc_get_histogram(fmc_context* c, unsigned long long* counts_host) {
   if (!c || !counts_host) return FMC_ERR_BAD_ARG;
   const long long len = fmc_histogram_len(c);
   if (len <= 0 || !c->hist) return FMC_ERR_STATE;
-  FMC_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
   FMC_CUDA(cudaMemcpyAsync(counts_host, c->hist, sizeof(unsigned long long) * len, cudaMemcpyDeviceToHost,
                            c->stream));
   FMC_CUDA(cudaStreamSynchronize(c->stream));
@@ -468,7 +539,8 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   if (!c || !params_start || nresample < 0) return FMC_ERR_BAD_ARG;
   if (c->model < 0) return FMC_ERR_NO_DATA;
   const ModelEntry& m = models()[c->model];
-  FMC_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
   if (c->inflight >= 0) FMC_CUDA(cudaStreamSynchronize(c->stream));
   const int P = m.nparam, Q = m.nprop;
   c->keep = keep_per_resample != 0;
@@ -532,6 +604,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   KernelArgs a;
   std::memset(&a, 0, sizeof(a));
   a.rows = c->rows_dev;
+  a.aux = m.naux > 0 ? c->aux_dev : nullptr;
   a.n = c->n;
   a.n_pad = c->n_pad;
   for (int i = 0; i < P; ++i) {
@@ -560,7 +633,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   }
 
   // data in shared memory when it fits (227 KB opt-in on B200), else through L1/L2
-  size_t shmem = sizeof(RowData) * (size_t)c->n_pad;
+  size_t shmem = (sizeof(RowData) + sizeof(double) * m.naux) * (size_t)c->n_pad;
   bool smem = shmem + 1024 <= (size_t)c->max_smem_optin;
   if (!smem) shmem = 0;
   const bool inject = z_inject_dev != nullptr;
@@ -569,9 +642,19 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   if (jac == fmc::JAC_ANALYTIC && !m.analytic) return FMC_ERR_BAD_ARG;  // double-only model_y, no model_grad
   const bool per_warp = c->mapping == FMC_FIT_PER_WARP;
   const fmc::WarpEntry wentry = per_warp ? fmc::fmc_warp_entry(c->model) : fmc::WarpEntry{nullptr, nullptr};
+  fmc::WarpArgs wa;
+  std::memset(&wa, 0, sizeof(wa));
   if (per_warp) {
     if (!wentry.launch) return FMC_ERR_BAD_MODEL;
-    FMC_CUDA(wentry.occupancy(inject, smem, jac, shmem, &bps));
+    // columns staged in shared memory: all four when they fit, else x and 1/err, else none
+    const size_t col = sizeof(double) * (size_t)c->n_w;
+    wa.stage = (4 + m.naux) * col + 1024 <= (size_t)c->max_smem_optin
+                   ? 4
+                   : ((2 + m.naux) * col + 1024 <= (size_t)c->max_smem_optin ? 2 : 0);
+    wa.cols = c->cols_dev;
+    wa.n_w = c->n_w;
+    shmem = wa.stage > 0 ? (wa.stage + m.naux) * col : 0;
+    FMC_CUDA(wentry.occupancy(inject, jac, shmem, &bps));
   } else {
     FMC_CUDA(m.occupancy(inject, smem, jac, shmem, &bps));
   }
@@ -624,6 +707,17 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     }
   }
 
+  if (per_warp) {
+    const long long need = full_grid * (FMC_WARP_THREADS / 32) * (long long)c->n_w;
+    if (need > c->tscratch_cap) {
+      cudaFree(c->tscratch_dev);
+      c->tscratch_dev = nullptr;
+      c->tscratch_cap = 0;
+      FMC_CUDA(cudaMalloc(&c->tscratch_dev, sizeof(double) * need));
+      c->tscratch_cap = need;
+    }
+    wa.tscratch = c->tscratch_dev;
+  }
   if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 2 * nchunks, c->stream));
   FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
   FMC_CUDA(cudaMemsetAsync(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP), c->stream));
@@ -656,7 +750,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     if (per_warp) {
       a.call = 0;
       a.next_id = c->counters_dev + 2 * ch;
-      FMC_CUDA(wentry.launch(a, inject, smem, jac, (int)grid, shmem, c->stream));
+      FMC_CUDA(wentry.launch(a, wa, inject, jac, (int)grid, shmem, c->stream));
     }
     for (int call = 0; call < 2 && !per_warp; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
       a.call = call;
@@ -732,7 +826,8 @@ int fmc_finish(fmc_context* c, double* sum_p, double* sum_p2, double* sum_prop, 
   if (c->inflight < 0) return FMC_ERR_STATE;
   const ModelEntry& m = models()[c->model];
   const int P = m.nparam, Q = m.nprop;
-  FMC_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
   std::vector<double> acc(acc_len(P, Q));
   FMC_CUDA(cudaMemcpyAsync(acc.data(), c->acc, sizeof(double) * acc.size(), cudaMemcpyDeviceToHost, c->stream));
   const long long nres = c->inflight;
@@ -763,7 +858,8 @@ int fmc_finish(fmc_context* c, double* sum_p, double* sum_p2, double* sum_prop, 
 int fmc_wait(fmc_context* c) {
   if (!c) return FMC_ERR_BAD_ARG;
   if (c->inflight < 0) return FMC_ERR_STATE;
-  FMC_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
   FMC_CUDA(cudaStreamSynchronize(c->stream));
   c->inflight = -1;
   return FMC_OK;
@@ -771,7 +867,8 @@ int fmc_wait(fmc_context* c) {
 
 int fmc_last_anomalies(fmc_context* c, long long* ids, int* flags, int cap) {
   if (!c) return FMC_ERR_BAD_ARG;
-  FMC_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
   unsigned long long h[1 + 2 * fmc::ANOM_CAP];
   FMC_CUDA(cudaMemcpy(h, c->anom_dev, sizeof(h), cudaMemcpyDeviceToHost));
   const int n = (int)h[0];
@@ -955,7 +1052,8 @@ int fmc_fit_once(int model, int ndata, const double* x, const double* y, const d
 int fmc_measure_dfma_peak(int device, int iters, double* tflops, float* ms_out) {
   if (!tflops || iters < 1) return FMC_ERR_BAD_ARG;
   if (device_count() <= 0) return FMC_ERR_NO_DEVICE;
-  FMC_CUDA(cudaSetDevice(device));
+  DeviceGuard guard_(device);
+  FMC_CUDA(guard_.err);
   cudaDeviceProp prop;
   FMC_CUDA(cudaGetDeviceProperties(&prop, device));
   const int threads = 256, blocks = prop.multiProcessorCount * 8;

@@ -17,6 +17,8 @@ struct ModelEntry {
   double (*model_y)(const double*, double);   // host copies of the plug-in routines
   void (*props)(const double*, double*);
   bool analytic;  // can form exact Jacobian rows (generic model_y or its own model_grad)
+  int naux;       // per-row auxiliary values the model declares (pass_eval.cuh), 0 = none
+  void (*row_aux)(double x, double* aux);
   // stage A (uniform first pass) and stage B (refill iterations) of one nl2sno call;
   // jac = JAC_FD (nl2sno) or JAC_ANALYTIC (nl2sol + madj)
   cudaError_t (*launch_init)(const KernelArgs&, bool inject, bool smem, int jac, size_t shmem, cudaStream_t);
@@ -33,6 +35,9 @@ template <class M>
 struct ModelBinding {
   static double host_model_y(const double* p, double x) { return M::model_y(p, x); }
   static void host_props(const double* p, double* q) { M::derived_properties(p, q); }
+  static void host_row_aux(double x, double* aux) {
+    if constexpr (model_naux<M>::value > 0) M::row_aux(x, aux);
+  }
 
   static constexpr bool kAnalytic = can_analytic_v<M>;
 
@@ -72,7 +77,7 @@ struct ModelBinding {
     });
   }
   static cudaError_t launch_jac0(const KernelArgs& a, double* rowJ, double* G0, cudaStream_t st) {
-    jac0_kernel<M><<<1, 1024, 0, st>>>(a, rowJ, G0);
+    jac0_kernel<M><<<1, FMC_JAC0_THREADS, 0, st>>>(a, rowJ, G0);
     return cudaGetLastError();
   }
   static cudaError_t launch_init_shared(const KernelArgs& a, const double* rowJ, const double* G0, bool inject,
@@ -120,6 +125,8 @@ struct ModelBinding {
       e.qnames[i] = qn[i];
     }
     e.analytic = kAnalytic;
+    e.naux = model_naux<M>::value;
+    e.row_aux = host_row_aux;
     e.model_y = host_model_y;
     e.props = host_props;
     e.launch_init = launch_init;

@@ -55,7 +55,10 @@ struct ModelPeaks10 {
     T y = params[0];
 #pragma unroll
     for (int kk = 0; kk < 3; ++kk) {
-      const T u = (x - params[2 + 3 * kk]) / params[3 + 3 * kk];
+      // 1/w is a function of the parameters alone: the compiler lifts it (and its perturbation) out
+      // of the loop over the data points, which then has no division left
+      const T rw = 1.0 / params[3 + 3 * kk];
+      const T u = (x - params[2 + 3 * kk]) * rw;
       y = y + params[1 + 3 * kk] * exp(-0.5 * (u * u));
     }
     return y;
@@ -81,9 +84,20 @@ struct ModelStiff4 {
     (*prop_name)[1] = "ac";
     for (int i = 0; i < 4; ++i) params_init[i] = 1.0;
   }
+  // x^(-d) = exp(-d log x): log x_i belongs to the data, not to the fit, so it is declared as a
+  // per-row auxiliary value (pass_eval.cuh) -- evaluated once per data point when the data are
+  // set instead of once per data point, pass and fit.
+  static constexpr int NAUX = 1;
+  FMC_HD static FMC_INLINE void row_aux(double x, double* aux) { aux[0] = log(x); }
   template <class T>
-  FMC_HD static FMC_INLINE T model_y(const T* params, double x) {
-    return params[0] * exp(-params[1] * x) + params[2] * pow(x, -params[3]);
+  FMC_HD static FMC_INLINE T model_y(const T* params, double x, const double* aux) {
+    return params[0] * exp(-params[1] * x) + params[2] * exp(-params[3] * aux[0]);
+  }
+  template <class T>
+  FMC_HD static FMC_INLINE T model_y(const T* params, double x) {  // the reference's argument list
+    double aux[NAUX];
+    row_aux(x, aux);
+    return model_y(params, x, aux);
   }
   FMC_HD static FMC_INLINE void derived_properties(const double* params, double* props) {
     props[0] = 0.6931471805599453 / params[1];

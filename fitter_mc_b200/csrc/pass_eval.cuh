@@ -61,6 +61,27 @@ struct has_dual_model<M, std::void_t<decltype(M::model_y(std::declval<const Dual
 template <class M>
 constexpr bool can_analytic_v = has_model_grad<M>::value || has_dual_model<M>::value;
 
+// Optional per-row auxiliary values: functions of the data abscissa x_i alone that the model needs
+// at every evaluation (e.g. log x_i for a power law x^(-d) = exp(-d log x_i)).  A plug-in declares
+//     static constexpr int NAUX = k;
+//     static void row_aux(double x, double* aux);                       // k values for one data point
+//     template <class T> static T model_y(const T* params, double x, const double* aux);
+// next to the reference-shaped model_y(params, x); the engine evaluates row_aux ONCE per data
+// point when the data are set (fmc_set_data) and keeps the values beside the rows, so data-only
+// transcendentals leave the (data points x passes x fits) loop.
+template <class M, class = void>
+struct model_naux : std::integral_constant<int, 0> {};
+template <class M>
+struct model_naux<M, std::void_t<decltype(M::NAUX)>> : std::integral_constant<int, M::NAUX> {};
+
+template <class M, class T>
+FMC_HD FMC_INLINE T eval_model(const T* params, double xi, const double* aux) {
+  if constexpr (model_naux<M>::value > 0)
+    return M::model_y(params, xi, aux);
+  else
+    return M::model_y(params, xi);
+}
+
 // An evaluation point with its finite-difference steps, held in registers for a whole pass.
 template <int P>
 struct PassPoint {
@@ -101,11 +122,21 @@ struct PassAcc {
 //    model is inlined p+1 times with all but one coordinate identical, so the compiler still
 //    shares common subexpressions (e.g. exp(-al*x) for every column except al's).
 //  * JAC_ANALYTIC: dm[k] = -d model_y / d params_k (the sign convention of the differences).
+//  `aux`: the row's auxiliary values (model_naux above); nullptr = evaluate them here (host images
+//  and one-off kernels; the fit kernels always pass the stored values).
 template <class M, int JAC = JAC_FD>
 FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, double& m0,
-                                 double (&dm)[M::NPARAM]) {
+                                 double (&dm)[M::NPARAM], const double* aux = nullptr) {
   constexpr int P = M::NPARAM;
-  m0 = M::model_y(pt.x, xi);
+  constexpr int NAUX = model_naux<M>::value;
+  double aux_here[NAUX > 0 ? NAUX : 1];
+  if constexpr (NAUX > 0) {
+    if (aux == nullptr) {
+      M::row_aux(xi, aux_here);
+      aux = aux_here;
+    }
+  }
+  m0 = eval_model<M>(pt.x, xi, aux);
   if constexpr (JAC == JAC_ANALYTIC && has_model_grad<M>::value) {
     double gr[P];
     M::model_grad(pt.x, xi, gr);
@@ -117,7 +148,7 @@ FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, doub
       Dual xs[P];
 #pragma unroll
       for (int m = 0; m < P; ++m) xs[m] = Dual(pt.x[m], (m == kk) ? 1.0 : 0.0, m == kk);
-      const Dual mk = M::model_y(xs, xi);
+      const Dual mk = eval_model<M>(xs, xi, aux);
       dm[kk] = -mk.d;
     }
   } else if constexpr (use_pert_v<M>) {
@@ -126,7 +157,7 @@ FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, doub
       Pert xs[P];
 #pragma unroll
       for (int m = 0; m < P; ++m) xs[m] = Pert(pt.x[m], (m == kk) ? pt.h[m] : 0.0, m == kk);
-      const Pert mk = M::model_y(xs, xi);
+      const Pert mk = eval_model<M>(xs, xi, aux);
       dm[kk] = -mk.d;
     }
   } else {
@@ -135,7 +166,7 @@ FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, doub
       double xs[P];
 #pragma unroll
       for (int m = 0; m < P; ++m) xs[m] = (m == kk) ? pt.x[m] + pt.h[m] : pt.x[m];
-      dm[kk] = m0 - M::model_y(xs, xi);
+      dm[kk] = m0 - eval_model<M>(xs, xi, aux);
     }
   }
 }
@@ -143,10 +174,19 @@ FMC_HD FMC_INLINE void row_model(const PassPoint<M::NPARAM>& pt, double xi, doub
 // Add one data point to the pass sums.  WITH_B: also J(b)^T r(a) for the secant update.
 template <class M, bool WITH_B, int JAC = JAC_FD>
 FMC_HD FMC_INLINE void row_accumulate(const PassPoint<M::NPARAM>& a, const PassPoint<M::NPARAM>& b,
-                                      double xi, double yfit, double rerr, PassAcc<M::NPARAM>& acc) {
+                                      double xi, double yfit, double rerr, PassAcc<M::NPARAM>& acc,
+                                      const double* aux = nullptr) {
   constexpr int P = M::NPARAM;
+  constexpr int NAUX = model_naux<M>::value;
+  double aux_here[NAUX > 0 ? NAUX : 1];
+  if constexpr (NAUX > 0) {  // (once for both points)
+    if (aux == nullptr) {
+      M::row_aux(xi, aux_here);
+      aux = aux_here;
+    }
+  }
   double m0, dma[P];
-  row_model<M, JAC>(a, xi, m0, dma);
+  row_model<M, JAC>(a, xi, m0, dma, aux);
   const double r = (yfit - m0) * rerr;  // madr, bootstrap.f90:247
   const double t = rerr * r;
   const double w2 = rerr * rerr;
@@ -164,7 +204,7 @@ FMC_HD FMC_INLINE void row_accumulate(const PassPoint<M::NPARAM>& a, const PassP
   }
   if (WITH_B) {
     double mb, dmb[P];
-    row_model<M, JAC>(b, xi, mb, dmb);
+    row_model<M, JAC>(b, xi, mb, dmb, aux);
 #pragma unroll
     for (int i = 0; i < P; ++i) acc.lky[i] = fma(dmb[i], t, acc.lky[i]);
   }

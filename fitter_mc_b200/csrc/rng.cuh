@@ -36,7 +36,8 @@ FMC_HD FMC_INLINE void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t&
 #endif
 }
 
-// Philox4x32-10 (Salmon et al., SC'11).  Known answers are checked in tests/test_rng.py.
+// Philox4x32-10 (Salmon et al., SC'11).  Known answers (Random123 kat_vectors) are checked on the host
+// image in tests/test_host_emul.py and on the device, bit for bit, in tests/test_gpu_rng.py.
 FMC_HD FMC_INLINE U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < FMC_PHILOX_ROUNDS; ++r) {

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(FMC_THREADS, 1) trial1_kernel(const KernelArgs
       const double yfit = fma(zz, rd.err, rd.y);
       // residual and Jacobian row at the trial point: as row_accumulate<M, false>
       double m0, dma[P];
-      row_model<M>(pa, rd.x, m0, dma);
+      row_model<M>(pa, rd.x, m0, dma, model_naux<M>::value > 0 ? a.aux + (i + m) * model_naux<M>::value : nullptr);
       const double r = (yfit - m0) * rd.rerr;
       const double t = rd.rerr * r;
       const double w2 = rd.rerr * rd.rerr;

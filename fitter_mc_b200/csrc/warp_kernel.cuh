@@ -1,25 +1,35 @@
-// One fit per WARP: the alternative mapping BASELINE.json's north star asks to be weighed
-// against one fit per thread ("one fit per thread or per warp, chosen by measurement").
+// One fit per WARP: the mapping for fits with many parameters and many data points (BASELINE.json
+// config C4: p = 10, n = 10^4), weighed against one fit per thread by measurement
+// (tools/gpu_mapping_bench.py).
 //
-// The 32 lanes of a warp share ONE resample.  A pass over the n data points is split between
-// them -- lane l takes the four-point groups l, l+32, l+64, ... (a group is what one counter
-// block of the generator serves, rng.cuh) -- and the per-lane partial sums (f, g, G, lky:
-// 1 + 2p + p(p+1)/2 doubles) are combined by a butterfly of warp shuffles, which leaves the
-// bitwise SAME totals in every lane.  Every lane then runs the (cheap, p x p) solver step on
-// those totals redundantly: identical inputs, identical control flow, no divergence, and no
-// lane ever waits for another fit.  Both nl2sno calls of fit_data and their initial passes run
-// inside the one kernel; warps take the next resample from the shared counter.
+// Why one fit per thread runs out of road at large p: the sums of a pass are 1 + 2p + p(p+1)/2
+// doubles (76 at p = 10 = 152 registers), the two evaluation points with their step-dependent
+// constants another ~90 registers, and the solver state 4.4 KB per fit -- the row loop of the
+// per-thread kernel compiles to 255 registers with the sums themselves spilled (78 local-memory
+// operations per data point), and 38 000 fits in flight keep 160 MB of solver state moving.
 //
-// Compared with one fit per thread (bootstrap_kernel.cuh): 32x fewer fits in flight (so 32x
-// less solver state), perfectly uniform control flow, rows read with unit stride across lanes
-// (coalesced when the data do not fit in shared memory); but the solver step is executed 32
-// times over and each pass pays 5 shuffle rounds per sum.  It pays when n x p is large (C4),
-// not for the small fits of C1/C2 -- which is to be confirmed by measurement: this path is
-// OPT-IN (fmc_set_fit_mapping) and, at the end of round 1, has been exercised only through its
-// host emulation (tests/host_emul, tests/test_warp_mapping.py), not yet on a GPU.
+// Here the 32 lanes of a warp share ONE resample:
+//  * rows are dealt to the lanes in groups of four (a group is what one counter block of the
+//    generator serves, rng.cuh): lane l takes groups l, l + 32, l + 64, ...  The data are stored
+//    once more in that order, one array per column ("lane-major": element s = (4 j + m) 32 + l is
+//    row 4 (32 j + l) + m), so that every load of a warp is one contiguous 256-byte segment.  x and
+//    1/err are staged in shared memory when they fit (all four columns when those fit too).
+//  * a trial pass is made in TWO SWEEPS over the warp's rows.  Sweep A evaluates the model and its
+//    differences at the trial point x: f, g = J^T r, G = J^T J (1 + p + p(p+1)/2 sums) and leaves
+//    t_i = r_i / err_i in a per-warp scratch row (L2 resident, one coalesced store).  Sweep B
+//    evaluates the differences at the previous point x0 and forms lky = J(x0)^T r(x) from the
+//    stored t_i (p sums).  Neither sweep holds the sums and the point-dependent constants of the
+//    other, which is what keeps the loops inside the register file; the FP64 work is the same as
+//    in one sweep.
+//  * the per-lane partial sums are combined by a butterfly of warp shuffles, which leaves the
+//    bitwise SAME totals in every lane; every lane then runs the (cheap, p x p) solver step on
+//    those totals redundantly: identical inputs, identical control flow, no divergence, and no
+//    lane ever waits for another fit.  Both nl2sno calls of fit_data and their initial passes run
+//    inside the one kernel; warps take the next resample from a shared counter.
 //
-// Sums are formed in a different order than in the per-thread kernels (32 partial sums, then
-// a tree), so results agree with them to rounding, not bitwise.
+// The deviates are the same function of (seed, resample, data point) as in the per-thread
+// kernels, so both mappings fit the same resampled data sets; sums are formed in a different
+// order (32 partial sums, then a tree), so results agree to rounding, not bitwise.
 #pragma once
 #include "bootstrap_kernel.cuh"
 
@@ -36,54 +46,174 @@ FMC_INLINE __device__ double warp_allsum(double v) {
   return v;
 }
 
-template <int P>
-FMC_INLINE __device__ void warp_allsum_acc(PassAcc<P>& acc, bool with_b) {
-  acc.f = warp_allsum(acc.f);
+// The columns of the data in lane-major order (see above); pointers are generic: shared memory
+// when the column was staged, global otherwise.
+struct WarpCols {
+  const double* x;
+  const double* y;
+  const double* err;
+  const double* rerr;
+  const double* aux;  // [NAUX][n_w] per-row auxiliary values of the model (pass_eval.cuh)
+};
+
+// the auxiliary values of row s, gathered from their columns
+template <class M>
+FMC_INLINE __device__ void warp_row_aux(const WarpCols& c, int n_w, int s, double (&ra)[model_naux<M>::value > 0 ? model_naux<M>::value : 1]) {
+  constexpr int NAUX = model_naux<M>::value;
 #pragma unroll
-  for (int i = 0; i < P; ++i) acc.g[i] = warp_allsum(acc.g[i]);
-#pragma unroll
-  for (int i = 0; i < P * (P + 1) / 2; ++i) acc.G[i] = warp_allsum(acc.G[i]);
-  if (with_b) {
-#pragma unroll
-    for (int i = 0; i < P; ++i) acc.lky[i] = warp_allsum(acc.lky[i]);
-  }
+  for (int k = 0; k < NAUX; ++k) ra[k] = c.aux[(size_t)k * n_w + s];
 }
 
-// The share of lane `lane` in one pass: groups lane, lane + 32, ... of four data points.
-template <class M, bool INJECT, bool WITH_B, int JAC>
-FMC_INLINE __device__ void warp_pass_loop(const RowData* __restrict__ rows, int n, int n_pad, int lane,
-                                          unsigned long long seed, unsigned long long id,
-                                          const double* __restrict__ zrow, const PassPoint<M::NPARAM>& pa,
-                                          const PassPoint<M::NPARAM>& pb, PassAcc<M::NPARAM>& acc) {
-  for (int i = 4 * lane; i < n_pad; i += 4 * 32) {
+// Sums of sweep A (f, g, G) and of sweep B (lky), kept apart so that each loop only carries its own.
+template <int P>
+struct SweepA {
+  static constexpr int PP = P * (P + 1) / 2;
+  double f, g[P], G[PP];
+  FMC_INLINE __device__ void zero() {
+    f = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) g[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < PP; ++i) G[i] = 0.0;
+  }
+  FMC_INLINE __device__ void allsum() {
+    f = warp_allsum(f);
+#pragma unroll
+    for (int i = 0; i < P; ++i) g[i] = warp_allsum(g[i]);
+#pragma unroll
+    for (int i = 0; i < PP; ++i) G[i] = warp_allsum(G[i]);
+  }
+};
+
+// Sweep A over the rows of lane `lane`: residual, Jacobian row and the sums at the point `pa`.
+// STORE_T: leave t_i = r_i / err_i in tbuf (lane-major) for sweep B.
+template <class M, bool INJECT, bool STORE_T, int JAC>
+FMC_INLINE __device__ void sweep_a(const WarpCols& c, int n, int n_w, int lane, unsigned long long seed,
+                                   unsigned long long id, const double* __restrict__ zrow,
+                                   const PassPoint<M::NPARAM>& pa, double* __restrict__ tbuf,
+                                   SweepA<M::NPARAM>& acc) {
+  constexpr int P = M::NPARAM;
+  constexpr int NAUX = model_naux<M>::value;
+  const int ngroup = n_w >> 7;  // groups of 4 rows per lane
+  for (int j = 0; j < ngroup; ++j) {
+    const int blk = 32 * j + lane;
     float z[4];
-    if (!INJECT) normals4(seed, id, (uint32_t)(i >> 2), z);
+    if (!INJECT) normals4(seed, id, (uint32_t)blk, z);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const RowData rd = rows[i + m];
+      const int s = (4 * j + m) * 32 + lane;
+      const double xi = c.x[s], yi = c.y[s], ei = c.err[s], wi = c.rerr[s];
       double zz;
       if (INJECT)
-        zz = (i + m < n) ? zrow[i + m] : 0.0;
+        zz = (4 * blk + m < n) ? zrow[4 * blk + m] : 0.0;
       else
         zz = (double)z[m];
-      const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
-      row_accumulate<M, WITH_B, JAC>(pa, pb, rd.x, yfit, rd.rerr, acc);
+      const double yfit = fma(zz, ei, yi);  // offset_data, bootstrap.f90:208
+      double m0, dma[P];
+      double ra[NAUX > 0 ? NAUX : 1];
+      warp_row_aux<M>(c, n_w, s, ra);
+      row_model<M, JAC>(pa, xi, m0, dma, ra);
+      const double r = (yfit - m0) * wi;  // madr, bootstrap.f90:247
+      const double t = wi * r;
+      const double w2 = wi * wi;
+      if (STORE_T) tbuf[s] = t;
+      acc.f = fma(r, r, acc.f);
+      int q = 0;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        acc.g[i] = fma(dma[i], t, acc.g[i]);
+        const double dw = dma[i] * w2;
+#pragma unroll
+        for (int jj = 0; jj <= i; ++jj) {
+          acc.G[q] = fma(dw, dma[jj], acc.G[q]);
+          ++q;
+        }
+      }
     }
   }
 }
 
-template <class M, bool INJECT, bool SMEM, int JAC>
-__global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const KernelArgs a) {
+// Sweep B: lky = J(pb)^T r(pa), from the t_i that sweep A left in tbuf.
+template <class M, int JAC>
+FMC_INLINE __device__ void sweep_b(const WarpCols& c, int n_w, int lane, const PassPoint<M::NPARAM>& pb,
+                                   const double* __restrict__ tbuf, double (&lky)[M::NPARAM]) {
+  constexpr int P = M::NPARAM;
+#pragma unroll
+  for (int i = 0; i < P; ++i) lky[i] = 0.0;
+#pragma unroll 4
+  for (int s = lane; s < n_w; s += 32) {
+    const double xi = c.x[s];
+    const double t = tbuf[s];
+    double mb, dmb[P];
+    double ra[model_naux<M>::value > 0 ? model_naux<M>::value : 1];
+    warp_row_aux<M>(c, n_w, s, ra);
+    row_model<M, JAC>(pb, xi, mb, dmb, ra);
+#pragma unroll
+    for (int i = 0; i < P; ++i) lky[i] = fma(dmb[i], t, lky[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) lky[i] = warp_allsum(lky[i]);
+}
+
+// Arguments of the warp kernel beyond KernelArgs.
+struct WarpArgs {
+  const double* cols;   // [4 + NAUX][n_w] lane-major x, y, err, 1/err, auxiliary values (global)
+  double* tscratch;     // [warps in the grid][n_w]
+  int n_w;              // rows padded to a multiple of 128 (padding: err = 1/err = 0)
+  int stage;            // staged in shared memory: 0 nothing, 2 x, 1/err and the auxiliary columns, 4 all
+};
+
+template <class M, bool INJECT, int JAC>
+__global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const KernelArgs a, const WarpArgs wa) {
   constexpr int P = M::NPARAM;
   constexpr int Q = M::NPROP;
+  constexpr int PP = P * (P + 1) / 2;
   constexpr int NM = 2 * (P + Q);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[FMC_WARP_THREADS / 32];
   __shared__ unsigned int sh_rc[16];
   if (threadIdx.x < 16) sh_rc[threadIdx.x] = 0u;
-  const RowData* rows = stage_rows<SMEM>(a, smem_raw);
+  const int n_w = wa.n_w;
+  WarpCols c;
+  {
+    // staged columns: x and 1/err first (both sweeps / the sums need them most), then y and err
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    const double* gx = wa.cols;
+    const double* gy = wa.cols + n_w;
+    const double* ge = wa.cols + 2 * (size_t)n_w;
+    const double* gw = wa.cols + 3 * (size_t)n_w;
+    const double* ga = wa.cols + 4 * (size_t)n_w;
+    constexpr int NAUX = model_naux<M>::value;
+    if (wa.stage >= 2) {
+      for (int i = threadIdx.x; i < n_w; i += blockDim.x) {
+        sm[i] = gx[i];
+        sm[n_w + i] = gw[i];
+      }
+      for (int i = threadIdx.x; i < NAUX * n_w; i += blockDim.x) sm[2 * n_w + i] = ga[i];
+      c.x = sm;
+      c.rerr = sm + n_w;
+      c.aux = sm + 2 * n_w;
+    } else {
+      c.x = gx;
+      c.rerr = gw;
+      c.aux = ga;
+    }
+    if (wa.stage >= 4) {
+      double* sm2 = sm + (size_t)(2 + NAUX) * n_w;
+      for (int i = threadIdx.x; i < n_w; i += blockDim.x) {
+        sm2[i] = gy[i];
+        sm2[n_w + i] = ge[i];
+      }
+      c.y = sm2;
+      c.err = sm2 + n_w;
+    } else {
+      c.y = gy;
+      c.err = ge;
+    }
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  double* tbuf = wa.tscratch + ((size_t)blockIdx.x * (FMC_WARP_THREADS / 32) + (threadIdx.x >> 5)) * (size_t)n_w;
 
   Nl2<P> s;
   double msum[NM], mcmp[NM];  // lane 0 of each warp carries the warp's moment sums
@@ -95,6 +225,45 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
   double cq[Q > 0 ? Q : 1];
   M::derived_properties(a.start, cq);
   unsigned int n_fit = 0, n_fcall = 0, n_gcall = 0, n_iter = 0, n_pass = 0;
+
+  // one pass at s.x (and, WITH_B, the J(x0)^T r(x) part), results into the solver
+  auto pass = [&](auto with_b, unsigned long long id, const double* zrow) {
+    constexpr bool WITH_B = decltype(with_b)::value;
+    double h1[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) h1[i] = JAC == JAC_ANALYTIC ? 1.0 : s.hA[i];
+    {
+      PassPoint<P> pa;
+      pa.set(s.x, h1);
+      SweepA<P> acc;
+      acc.zero();
+      sweep_a<M, INJECT, WITH_B, JAC>(c, a.n, n_w, lane, a.seed, id, zrow, pa, tbuf, acc);
+      acc.allsum();
+      s.res_f = acc.f;
+#pragma unroll
+      for (int i = 0; i < P; ++i) s.res_g[i] = JAC == JAC_ANALYTIC ? acc.g[i] : acc.g[i] * (1.0 / h1[i]);
+      int q = 0;
+#pragma unroll
+      for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int jj = 0; jj <= i; ++jj) {
+          s.res_G[q] = JAC == JAC_ANALYTIC ? acc.G[q] : acc.G[q] * ((1.0 / h1[i]) * (1.0 / h1[jj]));
+          ++q;
+        }
+    }
+    if constexpr (WITH_B) {
+      __syncwarp();  // the t_i of this warp's other lanes are not read, but keep the sweeps ordered
+      double hb[P];
+#pragma unroll
+      for (int i = 0; i < P; ++i) hb[i] = JAC == JAC_ANALYTIC ? 1.0 : s.hJ[i];
+      PassPoint<P> pb;
+      pb.set(s.x0, hb);
+      double lky[P];
+      sweep_b<M, JAC>(c, n_w, lane, pb, tbuf, lky);
+#pragma unroll
+      for (int i = 0; i < P; ++i) s.res_lky[i] = JAC == JAC_ANALYTIC ? lky[i] : lky[i] * (1.0 / hb[i]);
+    }
+  };
 
   for (;;) {
     unsigned long long kk = 0;
@@ -112,38 +281,12 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
     int cnt[10];
     for (int call = 0; call < 2; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
       s.begin(xs);
-      int passes = 0;
-      bool more;
-      {
-        // first evaluation of the call: residual + Jacobian at the starting point, D = 1
-        double h1[P];
-#pragma unroll
-        for (int i = 0; i < P; ++i) h1[i] = JAC == JAC_ANALYTIC ? 1.0 : s.hA[i];
-        PassPoint<P> pa;
-        pa.set(s.x, h1);
-        PassAcc<P> acc;
-        acc.zero();
-        warp_pass_loop<M, INJECT, false, JAC>(rows, a.n, a.n_pad, lane, a.seed, id, zrow, pa, pa, acc);
-        warp_allsum_acc<P>(acc, false);
-        if constexpr (JAC == JAC_ANALYTIC)
-          pass_finish_analytic<P>(acc, s);
-        else
-          pass_finish<P>(acc, s);
-        ++passes;
-        more = s.resume();
-      }
+      int passes = 1;
+      // first evaluation of the call: residual + Jacobian at the starting point, D = 1
+      pass(std::false_type{}, id, zrow);
+      bool more = s.resume();
       while (more) {
-        PassPoint<P> pa, pb;
-        pa.set(s.x, s.hA);
-        pb.set(s.x0, s.hJ);
-        PassAcc<P> acc;
-        acc.zero();
-        warp_pass_loop<M, INJECT, true, JAC>(rows, a.n, a.n_pad, lane, a.seed, id, zrow, pa, pb, acc);
-        warp_allsum_acc<P>(acc, true);
-        if constexpr (JAC == JAC_ANALYTIC)
-          pass_finish_analytic<P>(acc, s);
-        else
-          pass_finish<P>(acc, s);
+        pass(std::true_type{}, id, zrow);
         ++passes;
         more = s.resume();
         if (more && passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
@@ -227,40 +370,37 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
 
 // Host-side binding of one model to its warp-kernel instantiations (kernels_warp.cu).
 struct WarpEntry {
-  cudaError_t (*launch)(const KernelArgs&, bool inject, bool smem, int jac, int grid, size_t shmem, cudaStream_t);
-  cudaError_t (*occupancy)(bool inject, bool smem, int jac, size_t shmem, int* blocks_per_sm);
+  cudaError_t (*launch)(const KernelArgs&, const WarpArgs&, bool inject, int jac, int grid, size_t shmem,
+                        cudaStream_t);
+  cudaError_t (*occupancy)(bool inject, int jac, size_t shmem, int* blocks_per_sm);
 };
 
 template <class M>
 struct WarpBinding {
   static constexpr bool kAnalytic = can_analytic_v<M>;
   template <class F>
-  static cudaError_t dispatch(bool inject, bool smem, int jac, F&& f) {
+  static cudaError_t dispatch(bool inject, int jac, F&& f) {
     using JF = std::integral_constant<int, JAC_FD>;
     using JA = std::integral_constant<int, JAC_ANALYTIC>;
     if (jac == JAC_ANALYTIC) {
       if constexpr (kAnalytic) {
-        if (inject)
-          return smem ? f(std::true_type{}, std::true_type{}, JA{}) : f(std::true_type{}, std::false_type{}, JA{});
-        return smem ? f(std::false_type{}, std::true_type{}, JA{}) : f(std::false_type{}, std::false_type{}, JA{});
+        return inject ? f(std::true_type{}, JA{}) : f(std::false_type{}, JA{});
       } else {
         return cudaErrorNotSupported;
       }
     }
-    if (inject) return smem ? f(std::true_type{}, std::true_type{}, JF{}) : f(std::true_type{}, std::false_type{}, JF{});
-    return smem ? f(std::false_type{}, std::true_type{}, JF{}) : f(std::false_type{}, std::false_type{}, JF{});
+    return inject ? f(std::true_type{}, JF{}) : f(std::false_type{}, JF{});
   }
-  static cudaError_t launch(const KernelArgs& a, bool inject, bool smem, int jac, int grid, size_t shmem,
+  static cudaError_t launch(const KernelArgs& a, const WarpArgs& wa, bool inject, int jac, int grid, size_t shmem,
                             cudaStream_t st) {
-    return dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
-      warp_fit_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>
-          <<<grid, FMC_WARP_THREADS, shmem, st>>>(a);
+    return dispatch(inject, jac, [&](auto I, auto J) {
+      warp_fit_kernel<M, decltype(I)::value, decltype(J)::value><<<grid, FMC_WARP_THREADS, shmem, st>>>(a, wa);
       return cudaGetLastError();
     });
   }
-  static cudaError_t occupancy(bool inject, bool smem, int jac, size_t shmem, int* nb) {
-    return dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
-      auto kern = warp_fit_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>;
+  static cudaError_t occupancy(bool inject, int jac, size_t shmem, int* nb) {
+    return dispatch(inject, jac, [&](auto I, auto J) {
+      auto kern = warp_fit_kernel<M, decltype(I)::value, decltype(J)::value>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
       if (e != cudaSuccess) return e;
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, kern, FMC_WARP_THREADS, shmem);
@@ -269,6 +409,19 @@ struct WarpBinding {
   static WarpEntry entry() { return WarpEntry{launch, occupancy}; }
 };
 
-WarpEntry fmc_warp_entry(int model);  // kernels_warp.cu
+// kernels_warp.cu, one object per model
+WarpEntry fmc_warp_entry_model0();
+WarpEntry fmc_warp_entry_model1();
+WarpEntry fmc_warp_entry_model2();
+WarpEntry fmc_warp_entry_model3();
+inline WarpEntry fmc_warp_entry(int model) {
+  switch (model) {
+    case 0: return fmc_warp_entry_model0();
+    case 1: return fmc_warp_entry_model1();
+    case 2: return fmc_warp_entry_model2();
+    case 3: return fmc_warp_entry_model3();
+  }
+  return WarpEntry{nullptr, nullptr};
+}
 
 }  // namespace fmc

@@ -11,8 +11,9 @@ MODULE fmc_b200_bindings
   USE, INTRINSIC :: iso_c_binding
   IMPLICIT NONE
   PRIVATE
-  PUBLIC :: fmc_bootstrap_run, fmc_fit_once, fmc_generate_offsets, fmc_strerror_f, &
-    &fmc_model_count, fmc_default_seed
+  PUBLIC :: fmc_bootstrap_run, fmc_bootstrap_run_binned, fmc_fit_once, fmc_generate_offsets, &
+    &fmc_strerror_f, fmc_model_count, fmc_set_jacobian_mode, fmc_histogram_quantiles, &
+    &fmc_default_seed
 
   INTEGER(c_long_long), PARAMETER :: fmc_default_seed = 31415_c_long_long ! utils.f90:7
 

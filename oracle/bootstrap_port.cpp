@@ -51,13 +51,14 @@ inline double model_y(int model, const double* p, double x) {
     case 2: {
       double y = p[0];
       for (int k = 0; k < 3; ++k) {
-        double u = (x - p[2 + 3 * k]) / p[3 + 3 * k];
+        const double rw = 1.0 / p[3 + 3 * k];  // as written in csrc/models/models_bench.cuh
+        double u = (x - p[2 + 3 * k]) * rw;
         y = y + p[1 + 3 * k] * std::exp(-0.5 * (u * u));
       }
       return y;
     }
     case 3:
-      return p[0] * std::exp(-p[1] * x) + p[2] * std::pow(x, -p[3]);
+      return p[0] * std::exp(-p[1] * x) + p[2] * std::exp(-p[3] * std::log(x));  // x^(-d), as in models_bench.cuh
     default:
       return 0.0;
   }
@@ -86,14 +87,14 @@ inline void model_grad(int model, const double* p, double x, double* g) {
       g[0] = 1.0;
       for (int k = 0; k < 3; ++k) {
         const double A = p[1 + 3 * k], mu = p[2 + 3 * k], w = p[3 + 3 * k];
-        const double u = (x - mu) / w, gs = std::exp(-0.5 * (u * u));
+        const double rw = 1.0 / w, u = (x - mu) * rw, gs = std::exp(-0.5 * (u * u));
         g[1 + 3 * k] = gs;
-        g[2 + 3 * k] = A * gs * u / w;
-        g[3 + 3 * k] = A * gs * u * u / w;
+        g[2 + 3 * k] = A * gs * u * rw;
+        g[3 + 3 * k] = A * gs * u * u * rw;
       }
       break;
     case 3: {
-      const double e = std::exp(-p[1] * x), pw = std::pow(x, -p[3]);
+      const double e = std::exp(-p[1] * x), pw = std::exp(-p[3] * std::log(x));
       g[0] = e;
       g[1] = -p[0] * x * e;
       g[2] = pw;

@@ -57,10 +57,31 @@ def c4(n=10000):
     return _make(2, np.linspace(0, 10, n), lambda y: np.full_like(y, 0.1), 10000)
 
 
-def c5(n=1000, rel=0.05, floor=0.01):
+# C5 ("tune err until >= 10 % of fits end with NL2SOL codes 7-10, measured by the
+# oracle").  Measured with the oracle on 2000 resamples (tests/test_c5_stress.py pins it):
+#   err = 0.05|y| + 0.01 (the untuned recipe)   0.0 % codes 7-10, every fit 6-8 passes
+#   err = 12.5|y| + 1.0                          4.3 %
+#   err = 13|y| + 1.0  (C5_REL, C5_FLOOR)        23 %: 22 % singular convergence (7), the rest false
+#                                                convergence (8) and the evaluation / iteration limits
+#                                                (9, 10); 5 ... 500 passes per fit, mean 77
+# At that noise level the exponential term is not identifiable: the fit to the un-resampled data
+# itself sits in the degenerate basin (a ~ -8.6e3, b ~ 45: a spike at the first data points) and
+# resampled fits run along flat valleys (a down to -1e16) -- the regime in which the reference
+# averages whatever nl2sno returns (bootstrap.f90:215-226 never looks at iv(1)).  Parameters of
+# such fits are not reproducible between ANY two builds; their chi-squared is
+# (tests/test_c5_stress.py).  "c5mild" is the untuned recipe, used where per-fit parameter
+# parity is asserted.
+C5_REL, C5_FLOOR = 13.0, 1.0
+
+
+def c5(n=1000, rel=C5_REL, floor=C5_FLOOR):
     return _make(3, np.logspace(-1, np.log10(50), n), lambda y: rel * np.abs(y) + floor, 5000)
+
+
+def c5_mild(n=1000):
+    return c5(n, rel=0.05, floor=0.01)
 
 
 def dataset(name):
     return {"c1": (0,) + c1_probe(), "c2p3": (0,) + c2(0), "c2": (1,) + c2(1), "c4": (2,) + c4(),
-            "c5": (3,) + c5()}[name]
+            "c5": (3,) + c5(), "c5mild": (3,) + c5_mild()}[name]

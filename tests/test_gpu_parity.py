@@ -45,7 +45,7 @@ def _compare(name, got, want):
     assert sig <= SIGMA_MAX
 
 
-@pytest.mark.parametrize("name", ["c1", "c2p3", "c2", "c4", "c5"])
+@pytest.mark.parametrize("name", ["c1", "c2p3", "c2", "c4", "c5mild"])
 def test_unresampled_fit_matches_oracle(fmc, oracle, name):
     """bootstrap.f90:288-291 on the GPU (fmc_fit_once) vs the oracle's fit_data."""
     model, x, y, err = datasets.dataset(name)
@@ -59,7 +59,7 @@ def test_unresampled_fit_matches_oracle(fmc, oracle, name):
     assert rc[0] in (3, 4, 5, 6) and rc[1] in (3, 4, 5, 6)
 
 
-@pytest.mark.parametrize("name,nres", [("c1", 4096), ("c2p3", 1024), ("c2", 1024), ("c5", 1024), ("c4", 48)])
+@pytest.mark.parametrize("name,nres", [("c1", 4096), ("c2p3", 1024), ("c2", 1024), ("c5mild", 1024), ("c4", 1024)])
 def test_injected_resamples_per_fit_parity(fmc, oracle, name, nres):
     """Identical injected offsets to both codes: per-fit parameters, properties, moment sums."""
     model, x, y, err = datasets.dataset(name)
@@ -123,19 +123,26 @@ def test_resample_ids_not_launch_geometry_decide_the_fits(fmc, oracle):
     assert np.array_equal(whole["params"], again["params"])
 
 
-def test_ensemble_matches_reference_stream_statistics(fmc, oracle):
-    """North-star check 2: ensemble means and errors vs the reference's own serial
-    RANLUX+polar stream (different random numbers), within 3 combined standard errors."""
-    model, x, y, err = datasets.dataset("c1")
+@pytest.mark.parametrize("name,na,nb", [("c1", 200000, 20000), ("c2", 200000, 6000), ("c2p3", 100000, 6000),
+                                        ("c5mild", 100000, 6000), ("c4", 40000, 800)])
+def test_ensemble_matches_reference_stream_statistics(fmc, oracle, name, na, nb):
+    """North-star check 2 on every config: ensemble means and errors of the production path
+    (counter-based generator, na resamples) vs the reference's own serial RANLUX+polar stream
+    (different random numbers, nb resamples; bootstrap.f90:309-341), within 3 combined standard errors.
+    (The stress config C5 is compared distributionally: tests/test_c5_stress.py.)"""
+    model, x, y, err = datasets.dataset(name)
     start = _start(oracle, model, x, y, err)
-    na, nb = 200000, 20000
     got = fmc.monte_carlo_fit_data(x, y, err, model, nrand_points=na, params_init=start, initial_fit=False)
     oracle.initialise_rng()
-    ref = oracle.bootstrap(model, x, y, err, start, nb, per_resample=False)
+    ref = oracle.bootstrap(model, x, y, err, start, nb, per_resample=False, nthreads=8)
     rm, rs = oracle.finalise_moments(nb, ref["sum_p"], ref["sum_p2"])
     gm, gs = got["params_opt"], got["err_params_opt"]
-    assert (np.abs(gm - rm) <= 3 * np.sqrt(gs ** 2 / na + rs ** 2 / nb)).all(), (gm, rm)
-    assert (np.abs(gs - rs) <= 3.5 * rs * np.sqrt(0.5 / na + 0.5 / nb)).all(), (gs, rs)
+    zm = (gm - rm) / np.sqrt(gs ** 2 / na + rs ** 2 / nb)
+    zs = (gs - rs) / (rs * np.sqrt(0.5 / na + 0.5 / nb))
+    print("\n[ensemble %s] gpu n=%d vs RANLUX-stream oracle n=%d: mean deviations %s se ; error-bar deviations %s se"
+          % (name, na, nb, np.round(zm, 2).tolist(), np.round(zs, 2).tolist()))
+    assert (np.abs(zm) <= 3.0).all(), (gm, rm)
+    assert (np.abs(zs) <= 3.5).all(), (gs, rs)
     qm, qs = oracle.finalise_moments(nb, ref["sum_prop"], ref["sum_prop2"])
     assert (np.abs(got["props_opt"] - qm) <= 3 * np.sqrt(got["err_props_opt"] ** 2 / na + qs ** 2 / nb)).all()
 

@@ -42,10 +42,10 @@ def test_sm_100a_only(usage):
 def test_refill_kernels_of_small_models_do_not_spill(usage, model, solver_stack):
     # iterate_kernel<M, INJECT=0, SMEM=1, JAC_FD, TRIAL1=0>: the kernel bench.py times
     regs, stack = _find(usage, "iterate_kernelINS_" + model + "ELb0ELb1ELi0ELb0E")
-    assert regs <= 232 and regs * 256 <= 65536
+    assert regs * 256 <= 65536
     assert stack == solver_stack                                     # the solver's arrays, no spill slots
     regs_a, stack_a = _find(usage, "iterate_kernelINS_" + model + "ELb0ELb1ELi1ELb0E")   # analytic mode
-    assert regs_a <= 232 and stack_a == solver_stack
+    assert regs_a * 256 <= 65536 and stack_a == solver_stack
 
 
 def test_uniform_kernels_are_light(usage):
@@ -55,3 +55,11 @@ def test_uniform_kernels_are_light(usage):
     assert regs <= 128 and stack <= 16
     regs, stack = _find(usage, "hist_kernel")
     assert regs <= 40 and stack == 0
+
+
+@pytest.mark.parametrize("model", ["9ModelUser", "10ModelTest4", "12ModelPeaks10", "11ModelStiff4"])
+def test_shared_jacobian_kernel_fits_its_launch(usage, model):
+    # jac0_kernel is launched <<<1, 256>>> (model_registry.cuh): registers x threads must fit one SM's
+    # register file whatever the plug-in's row_model needs (round-1 advisor finding: 72 x 1024 did not)
+    regs, stack = _find(usage, "jac0_kernelINS_" + model)
+    assert regs * 256 <= 65536

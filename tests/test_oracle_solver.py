@@ -158,7 +158,7 @@ def _scipy_fit(model, x, y, err, p0):
     return least_squares(f, p0, method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15, x_scale="jac").x
 
 
-@pytest.mark.parametrize("name", ["c1", "c2p3", "c2", "c4", "c5"])
+@pytest.mark.parametrize("name", ["c1", "c2p3", "c2", "c4", "c5mild"])
 def test_fit_matches_scipy(oracle, name):
     model, x, y, err = datasets.dataset(name)
     info = oracle.model_info(model)

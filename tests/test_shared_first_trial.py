@@ -26,7 +26,7 @@ def _d(a):
     return a.ctypes.data_as(_dp)
 
 
-@pytest.mark.parametrize("name,nres", [("c1", 400), ("c2", 80), ("c5", 80), ("c4", 6)])
+@pytest.mark.parametrize("name,nres", [("c1", 400), ("c2", 80), ("c5mild", 80), ("c4", 6)])
 def test_shared_first_trial_host_image(emul, oracle, name, nres):
     model, x, y, err = datasets.dataset(name)
     info = oracle.model_info(model)
@@ -74,7 +74,7 @@ np.save(%(path)r, out["params"])
 @pytest.mark.skipif(os.environ.get("FMC_TEST_TRIAL1_PATH") != "1",
                     reason="shared-first-trial kernels not yet run on a GPU (set FMC_TEST_TRIAL1_PATH=1)")
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("name,nres", [("c1", 20000), ("c2", 5000), ("c5", 2000)])
+@pytest.mark.parametrize("name,nres", [("c1", 20000), ("c2", 5000), ("c5mild", 2000)])
 def test_cuda_shared_first_trial_equals_default_path(tmp_path, name, nres):
     res = {}
     for flag in ("0", "1"):                       # the switch is read when a context is created: fresh processes

@@ -17,7 +17,7 @@ import oracle_lib as oracle  # noqa: E402
 
 def main():
     out = {}
-    for name in ("c2", "c1", "c5"):
+    for name in ("c2", "c1", "c5mild"):
         model, x, y, err = datasets.dataset(name)
         info = fmc.initialise_model(model)
         start, _ = oracle.fit_data(model, x, y, err, info["params_init"])

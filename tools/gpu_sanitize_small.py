@@ -15,6 +15,6 @@ z = fmc.generate_offsets(31415, 0, 700, len(x))
 b = fmc.monte_carlo_fit_data(x, y, err, model, nrand_points=700, params_init=start, initial_fit=False, per_resample=True,
                              z_inject=z)
 assert np.array_equal(a["params"], b["params"])
-m3, x3, y3, e3 = datasets.dataset("c5")
+m3, x3, y3, e3 = datasets.dataset("c5mild")
 c = fmc.monte_carlo_fit_data(x3[:200], y3[:200], e3[:200], m3, nrand_points=300, per_resample=True)
 print("sanitize run ok", a["params_opt"], c["params_opt"])
