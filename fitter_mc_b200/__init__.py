@@ -18,10 +18,13 @@ from .api import (  # noqa: F401
     histogram_quantiles,
     histogram_range_from_pilot,
     initialise_model,
+    last_combine_method,
     lib,
     lib_path,
     measure_dfma_peak,
     model_count,
     model_y,
     monte_carlo_fit_data,
+    nccl_available,
+    nccl_unique_id,
 )

@@ -59,12 +59,14 @@ def lib():
                                     C.c_longlong, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _lp, _lp]
     L.fmc_fit_once.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _ip]
     L.fmc_generate_offsets.argtypes = [C.c_ulonglong, C.c_longlong, C.c_longlong, C.c_int, _dp]
+    L.fmc_debug_philox4x32.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.fmc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.fmc_destroy.argtypes = [C.c_void_p]
     L.fmc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.fmc_set_data.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]
     L.fmc_set_accumulator_dev.argtypes = [C.c_void_p, C.c_void_p]
     L.fmc_accumulator_len.argtypes = [C.c_void_p]
+    L.fmc_get_accumulator.argtypes = [C.c_void_p, _dp]
     L.fmc_launch.argtypes = [C.c_void_p, _dp, C.c_longlong, C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_int]
     L.fmc_finish.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _lp, _lp]
     L.fmc_wait.argtypes = [C.c_void_p]
@@ -73,11 +75,18 @@ def lib():
     L.fmc_last_kernel_ms.restype = C.c_float
     L.fmc_last_kernel_ms.argtypes = [C.c_void_p]
     L.fmc_last_launch_geometry.argtypes = [C.c_void_p, _ip]
+    L.fmc_last_launch_count.restype = C.c_longlong
+    L.fmc_last_launch_count.argtypes = [C.c_void_p]
     L.fmc_measure_dfma_peak.argtypes = [C.c_int, C.c_int, _dp, C.POINTER(C.c_float)]
     L.fmc_finalise_moments.argtypes = [C.c_int, C.c_longlong, _dp, _dp, _dp, _dp]
     L.fmc_bootstrap_run_binned.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, C.c_ulonglong,
                                            C.c_longlong, C.c_int, _dp, _dp, _dp, _dp, _lp, _lp, C.c_int, _dp, _dp,
                                            C.c_void_p]
+    L.fmc_nccl_available.restype = C.c_int
+    L.fmc_nccl_unique_id.argtypes = [C.c_char_p]
+    L.fmc_nccl_init_rank.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.fmc_allreduce.argtypes = [C.c_void_p]
+    L.fmc_last_combine_method.restype = C.c_int
     L.fmc_set_fit_mapping.argtypes = [C.c_void_p, C.c_int]
     L.fmc_set_jacobian_mode.argtypes = [C.c_void_p, C.c_int]
     L.fmc_model_has_analytic_jacobian.argtypes = [C.c_int]
@@ -164,6 +173,15 @@ def generate_offsets(seed, first_counter, nresample, ndata):
     z = np.empty((nresample, ndata))
     _check(lib().fmc_generate_offsets(seed, first_counter, nresample, ndata, _d(z)), "fmc_generate_offsets")
     return z
+
+
+def debug_philox4x32(counters_keys):
+    """Raw words of the device generator: counters_keys uint32 [n][6] (c0..c3, k0, k1) -> uint32 [n][4]."""
+    ck = np.ascontiguousarray(counters_keys, dtype=np.uint32).reshape(-1, 6)
+    out = np.zeros((len(ck), 4), dtype=np.uint32)
+    _check(lib().fmc_debug_philox4x32(ck.ctypes.data_as(C.c_void_p), len(ck), out.ctypes.data_as(C.c_void_p)),
+           "fmc_debug_philox4x32")
+    return out
 
 
 def decode_accumulator(model, params_start, acc):
@@ -267,6 +285,23 @@ def histogram_range_from_pilot(values, nsigma=8.0):
     return m - nsigma * sd, m + nsigma * sd
 
 
+def nccl_available():
+    """0 if libnccl.so.2 cannot be loaded, else NCCL's version code."""
+    return int(lib().fmc_nccl_available())
+
+
+def nccl_unique_id():
+    """128 bytes for rank 0 to broadcast to the other ranks (Context.nccl_init_rank)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().fmc_nccl_unique_id(buf), "fmc_nccl_unique_id")
+    return buf.raw
+
+
+def last_combine_method():
+    """How the last one-call multi-GPU run combined its GPUs: "none", "nccl" or "host"."""
+    return {0: "none", 1: "nccl", 2: "host"}[int(lib().fmc_last_combine_method())]
+
+
 def measure_dfma_peak(device=0, iters=20000):
     """Measured FP64 FMA peak of the device in TFLOP/s (register-resident DFMA chains)."""
     t = C.c_double(0.0)
@@ -308,6 +343,12 @@ class Context:
     def accumulator_len(self):
         return lib().fmc_accumulator_len(self._h)
 
+    def read_accumulator(self):
+        """The accumulator block on the host, after the work queued so far (launch, allreduce)."""
+        acc = np.zeros(self.accumulator_len())
+        _check(lib().fmc_get_accumulator(self._h, _d(acc)), "fmc_get_accumulator")
+        return acc
+
     def set_accumulator_dev(self, ptr):
         _check(lib().fmc_set_accumulator_dev(self._h, C.c_void_p(ptr)), "fmc_set_accumulator_dev")
 
@@ -334,6 +375,16 @@ class Context:
 
     def wait(self):
         _check(lib().fmc_wait(self._h), "fmc_wait")
+
+    def nccl_init_rank(self, unique_id, nranks, rank):
+        """Bind this GPU as rank `rank` of `nranks` (unique_id: nccl_unique_id() of rank 0)."""
+        assert len(unique_id) == 128
+        _check(lib().fmc_nccl_init_rank(self._h, unique_id, int(nranks), int(rank)), "fmc_nccl_init_rank")
+
+    def allreduce(self):
+        """The single collective of the path: one ncclAllReduce of the accumulator block (and of the
+        binned counts) over the bound ranks, enqueued on the context's stream after launch()."""
+        _check(lib().fmc_allreduce(self._h), "fmc_allreduce")
 
     def set_jacobian_mode(self, mode):
         """"forward-difference" (nl2sno, the reference's path; default) or "analytic" (nl2sol + madj,
@@ -383,6 +434,10 @@ class Context:
 
     def kernel_ms(self):
         return float(lib().fmc_last_kernel_ms(self._h))
+
+    def launch_count(self):
+        """Kernels of this library that the last launch() enqueued."""
+        return int(lib().fmc_last_launch_count(self._h))
 
     def geometry(self):
         g = np.zeros(4, dtype=np.int32)

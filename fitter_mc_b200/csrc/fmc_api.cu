@@ -10,6 +10,9 @@
 #include <thread>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and constants only: the library is loaded at run time (see NcclApi below)
+
 #include "../../include/fmc_b200.h"
 #include "model_registry.cuh"
 #include "trial1_kernel.cuh"
@@ -44,6 +47,14 @@ int g_default_mapping = 0;  // fit mapping of the one-call entry points (fmc_set
     }                                                                                    \
   } while (0)
 
+// a kernel launch of the fit pipeline: counted, so that callers can report how many of this
+// library's kernels ran (fmc_last_launch_count)
+#define FMC_LAUNCH(call) \
+  do {                   \
+    FMC_CUDA(call);      \
+    ++c->nlaunch;        \
+  } while (0)
+
 // temporary device buffer, released on every return path
 struct DevBuf {
   double* p = nullptr;
@@ -67,6 +78,62 @@ struct DeviceGuard {
     if (prev >= 0 && prev != dev) cudaSetDevice(prev);
   }
 };
+
+// NCCL, bound at run time: the moment accumulators of the GPUs of one box are combined by ONE
+// ncclAllReduce over NVLink, replacing the OpenMP REDUCTION(+) of
+// bootstrap.f90:310-311.  dlopen instead of a link-time dependency, so that a process that has
+// already loaded an NCCL (torch ships its own libnccl.so.2) shares that copy, and a single-GPU
+// host without NCCL can still load libfmc_b200.so.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  bool ok = false;
+};
+
+const NcclApi& nccl() {
+  static const NcclApi api = [] {
+    NcclApi a;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (a.handle) break;
+    }
+    if (!a.handle) return a;
+    auto sym = [&](const char* n) { return dlsym(a.handle, n); };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommInitAll = (decltype(a.CommInitAll))sym("ncclCommInitAll");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    a.GetVersion = (decltype(a.GetVersion))sym("ncclGetVersion");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllReduce && a.GroupStart &&
+           a.GroupEnd && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
+
+#define FMC_NCCL(call)                                                                   \
+  do {                                                                                   \
+    ncclResult_t r_ = (call);                                                            \
+    if (r_ != ncclSuccess) {                                                             \
+      g_last_cuda_error = std::string(#call) + ": " + nccl().GetErrorString(r_);         \
+      return FMC_ERR_NCCL;                                                               \
+    }                                                                                    \
+  } while (0)
+
+int g_last_combine = FMC_COMBINE_NONE;  // how the last multi-GPU one-call run combined its accumulators
 
 const std::vector<ModelEntry>& models() {
   static const std::vector<ModelEntry> m = {fmc::fmc_entry_model0(), fmc::fmc_entry_model1(),
@@ -96,6 +163,22 @@ __global__ void generate_offsets_kernel(unsigned long long seed, long long first
     normals4(seed, (unsigned long long)(first + r), (uint32_t)b, zz);
     for (int m = 0; m < 4 && 4 * b + m < n; ++m) z[r * n + 4 * b + m] = (double)zz[m];
   }
+}
+
+// Raw words of the counter-based generator for known-answer tests on the device (fmc_debug_philox4x32).
+__global__ void philox_debug_kernel(const uint32_t* __restrict__ in6, int n, uint32_t* __restrict__ out4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fmc::U4 c;
+  c.x = in6[6 * i];
+  c.y = in6[6 * i + 1];
+  c.z = in6[6 * i + 2];
+  c.w = in6[6 * i + 3];
+  const fmc::U4 o = fmc::philox4x32_10(c, in6[6 * i + 4], in6[6 * i + 5]);
+  out4[4 * i] = o.x;
+  out4[4 * i + 1] = o.y;
+  out4[4 * i + 2] = o.z;
+  out4[4 * i + 3] = o.w;
 }
 
 // Register-resident DFMA chains: the measured FP64 roofline denominator (MEASURED_PEAKS.json
@@ -179,6 +262,9 @@ struct fmc_context {
   unsigned long long* hist = nullptr;
   long long hist_own_cap = 0;
   int hist_bins = 0;
+  ncclComm_t comm = nullptr;  // communicator of this GPU's rank (fmc_nccl_init_rank / the one-call multi-GPU run)
+  bool comm_owned = false;
+  int comm_nranks = 1;
   int jac = fmc::JAC_FD;  // how Jacobian rows are formed (fmc_set_jacobian_mode)
   int mapping = 0;        // 0 = one fit per thread, 1 = one fit per warp (fmc_set_fit_mapping)
   bool shared_first_trial = false;  // experimental, FMC_SHARED_FIRST_TRIAL=1 (trial1_kernel.cuh)
@@ -189,6 +275,7 @@ struct fmc_context {
   long long rowj_cap = 0;
   int ncounters = 0;
   long long inflight = -1;
+  long long nlaunch = 0;  // kernels launched by the last fmc_launch
   bool keep = false;
   double start[16] = {0};
   int geom[4] = {0, 0, 0, 0};
@@ -211,6 +298,7 @@ const char* fmc_strerror(int code) {
     case FMC_ERR_NO_DATA: return "fmc_set_data has not been called";
     case FMC_ERR_STATE: return "no launch in flight";
     case FMC_ERR_ALLOC: return "allocation failed";
+    case FMC_ERR_NCCL: return "an NCCL call failed or NCCL could not be loaded (see fmc_last_cuda_error)";
     default: return "unknown error code";
   }
 }
@@ -299,6 +387,7 @@ int fmc_destroy(fmc_context* c) {
   if (!c) return FMC_OK;
   DeviceGuard guard_(c->device);
   if (c->inflight >= 0) cudaStreamSynchronize(c->stream);
+  if (c->comm && c->comm_owned && nccl().ok) nccl().CommDestroy(c->comm);
   cudaFree(c->rows_dev);
   cudaFree(c->cols_dev);
   cudaFree(c->aux_dev);
@@ -724,7 +813,8 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   if (binning)
     FMC_CUDA(cudaMemsetAsync(h.hist, 0, sizeof(unsigned long long) * (size_t)(P + Q) * (h.bins + 2), c->stream));
   FMC_CUDA(cudaEventRecord(c->ev0, c->stream));
-  if (shared_init && nresample > 0) FMC_CUDA(m.launch_jac0(a, c->rowj_dev, g0_dev, c->stream));
+  c->nlaunch = 0;
+  if (shared_init && nresample > 0) FMC_LAUNCH(m.launch_jac0(a, c->rowj_dev, g0_dev, c->stream));
   for (long long ch = 0; ch < nchunks; ++ch) {
     const long long lo = ch * cap, cnt = (nresample - lo) < cap ? (nresample - lo) : cap;
     a.first = first_counter + lo;
@@ -750,23 +840,23 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     if (per_warp) {
       a.call = 0;
       a.next_id = c->counters_dev + 2 * ch;
-      FMC_CUDA(wentry.launch(a, wa, inject, jac, (int)grid, shmem, c->stream));
+      FMC_LAUNCH(wentry.launch(a, wa, inject, jac, (int)grid, shmem, c->stream));
     }
     for (int call = 0; call < 2 && !per_warp; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
       a.call = call;
       a.next_id = c->counters_dev + 2 * ch + call;
       if (call == 0 && shared_init)
-        FMC_CUDA(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
+        FMC_LAUNCH(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
       else
-        FMC_CUDA(m.launch_init(a, inject, smem, jac, shmem, c->stream));
+        FMC_LAUNCH(m.launch_init(a, inject, smem, jac, shmem, c->stream));
       if (call == 0 && trial1) {
-        FMC_CUDA(t1.launch_trial1(a, c->rowj_dev, c->trial1_dev, inject, shmem_shared, c->stream));
+        FMC_LAUNCH(t1.launch_trial1(a, c->rowj_dev, c->trial1_dev, inject, shmem_shared, c->stream));
         a.trial1 = c->trial1_dev;
-        FMC_CUDA(t1.launch_iter(a, inject, (int)grid, shmem, c->stream));
+        FMC_LAUNCH(t1.launch_iter(a, inject, (int)grid, shmem, c->stream));
         a.trial1 = nullptr;
         continue;
       }
-      FMC_CUDA(m.launch_iter(a, inject, smem, jac, (int)grid, shmem, c->stream));
+      FMC_LAUNCH(m.launch_iter(a, inject, smem, jac, (int)grid, shmem, c->stream));
     }
     if (binning) {
       h.params = a.params_out;
@@ -778,7 +868,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
       if (hgrid > hmax) hgrid = hmax;
       if (hgrid < 1) hgrid = 1;
       hist_kernel<<<(unsigned)hgrid, 256, 0, c->stream>>>(h);
-      FMC_CUDA(cudaGetLastError());
+      FMC_LAUNCH(cudaGetLastError());
     }
   }
   FMC_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -865,6 +955,18 @@ int fmc_wait(fmc_context* c) {
   return FMC_OK;
 }
 
+int fmc_get_accumulator(fmc_context* c, double* acc_host) {
+  if (!c || !acc_host) return FMC_ERR_BAD_ARG;
+  if (c->model < 0) return FMC_ERR_NO_DATA;
+  const ModelEntry& m = models()[c->model];
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
+  FMC_CUDA(cudaMemcpyAsync(acc_host, c->acc, sizeof(double) * acc_len(m.nparam, m.nprop), cudaMemcpyDeviceToHost,
+                           c->stream));
+  FMC_CUDA(cudaStreamSynchronize(c->stream));
+  return FMC_OK;
+}
+
 int fmc_last_anomalies(fmc_context* c, long long* ids, int* flags, int cap) {
   if (!c) return FMC_ERR_BAD_ARG;
   DeviceGuard guard_(c->device);
@@ -886,11 +988,70 @@ float fmc_last_kernel_ms(fmc_context* c) {
   return ms;
 }
 
+long long fmc_last_launch_count(const fmc_context* c) { return c ? c->nlaunch : -1; }
+
 int fmc_last_launch_geometry(const fmc_context* c, int* out4) {
   if (!c || !out4) return FMC_ERR_BAD_ARG;
   for (int i = 0; i < 4; ++i) out4[i] = c->geom[i];
   return FMC_OK;
 }
+
+// ---------------------------------------------------------------------------- NCCL combine
+int fmc_nccl_available(void) {
+  if (!nccl().ok) return 0;
+  int v = 0;
+  if (nccl().GetVersion && nccl().GetVersion(&v) == ncclSuccess) return v;
+  return 1;
+}
+
+int fmc_nccl_unique_id(char* id128) {
+  if (!id128) return FMC_ERR_BAD_ARG;
+  if (!nccl().ok) {
+    g_last_cuda_error = "libnccl.so.2 could not be loaded";
+    return FMC_ERR_NCCL;
+  }
+  static_assert(NCCL_UNIQUE_ID_BYTES == 128, "fmc_nccl_unique_id hands out 128 bytes");
+  ncclUniqueId id;
+  FMC_NCCL(nccl().GetUniqueId(&id));
+  std::memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+  return FMC_OK;
+}
+
+int fmc_nccl_init_rank(fmc_context* c, const char* id128, int nranks, int rank) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return FMC_ERR_BAD_ARG;
+  if (!nccl().ok) {
+    g_last_cuda_error = "libnccl.so.2 could not be loaded";
+    return FMC_ERR_NCCL;
+  }
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
+  if (c->comm && c->comm_owned) nccl().CommDestroy(c->comm);
+  c->comm = nullptr;
+  ncclUniqueId id;
+  std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+  FMC_NCCL(nccl().CommInitRank(&c->comm, nranks, id, rank));
+  c->comm_owned = true;
+  c->comm_nranks = nranks;
+  return FMC_OK;
+}
+
+int fmc_allreduce(fmc_context* c) {
+  if (!c) return FMC_ERR_BAD_ARG;
+  if (c->model < 0) return FMC_ERR_NO_DATA;
+  if (!c->comm || c->comm_nranks <= 1) return FMC_OK;  // a single rank: nothing to combine
+  const ModelEntry& m = models()[c->model];
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
+  // ONE all-reduce of the accumulator block (moment sums, return-code histogram, counters: all doubles)
+  FMC_NCCL(nccl().AllReduce(c->acc, c->acc, (size_t)acc_len(m.nparam, m.nprop), ncclDouble, ncclSum, c->comm,
+                            c->stream));
+  if (c->hist_bins > 0 && c->hist)  // optional binned distributions: integer counts, exact in any order
+    FMC_NCCL(nccl().AllReduce(c->hist, c->hist, (size_t)(m.nparam + m.nprop) * (c->hist_bins + 2), ncclUint64,
+                              ncclSum, c->comm, c->stream));
+  return FMC_OK;
+}
+
+int fmc_last_combine_method(void) { return g_last_combine; }
 
 // ---------------------------------------------------------------------------- one-shot API
 namespace {
@@ -906,6 +1067,28 @@ int cached_context(int device, fmc_context** out) {
   }
   *out = g_ctx[device];
   return FMC_OK;
+}
+
+// one communicator per GPU for the in-process multi-GPU run over devices 0..G-1, created once
+std::vector<std::vector<ncclComm_t>> g_comms;
+ncclComm_t* cached_comms(int G) {
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  if ((int)g_comms.size() <= G) g_comms.resize(G + 1);
+  if (g_comms[G].empty()) {
+    std::vector<ncclComm_t> comms(G, nullptr);
+    std::vector<int> devs(G);
+    for (int g = 0; g < G; ++g) devs[g] = g;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    const ncclResult_t r = nccl().CommInitAll(comms.data(), G, devs.data());
+    if (prev >= 0) cudaSetDevice(prev);
+    if (r != ncclSuccess) {
+      g_last_cuda_error = std::string("ncclCommInitAll: ") + nccl().GetErrorString(r);
+      return nullptr;
+    }
+    g_comms[G] = comms;
+  }
+  return g_comms[G].data();
 }
 }  // namespace
 
@@ -982,14 +1165,53 @@ int bootstrap_run_impl(int model, int ndata, const double* x, const double* y, c
       g_last_cuda_error = errs[g];
       return rcs[g];
     }
-  // combine the per-GPU accumulator blocks (what an all-reduce does across ranks)
   std::vector<double> acc(AL, 0.0);
-  for (int g = 0; g < G; ++g)
-    for (int i = 0; i < AL; ++i) acc[i] += accs[g][i];
-  if (HL > 0 && counts) {
-    for (size_t i = 0; i < HL; ++i) counts[i] = 0ULL;
+  g_last_combine = FMC_COMBINE_NONE;
+  if (G > 1) {
+    // Combine the per-GPU accumulator blocks: ONE ncclAllReduce over NVLink, issued for all GPUs of the
+    // box as one group on their own streams (bootstrap.f90:310-311's REDUCTION(+), across GPUs); every
+    // GPU then holds the total and GPU 0's copy is read back.  Without a loadable NCCL the blocks
+    // (31 doubles each) are added on the host instead; fmc_last_combine_method() says which.
+    std::vector<fmc_context*> ctxs(G, nullptr);
     for (int g = 0; g < G; ++g)
-      for (size_t i = 0; i < HL; ++i) counts[i] += hists[g][i];
+      if (cached_context(g, &ctxs[g]) != FMC_OK) return FMC_ERR_CUDA;
+    ncclComm_t* comms = nccl().ok ? cached_comms(G) : nullptr;
+    if (comms) {
+      ncclResult_t r = nccl().GroupStart();
+      for (int g = 0; g < G && r == ncclSuccess; ++g) {
+        fmc_context* c = ctxs[g];
+        r = nccl().AllReduce(c->acc, c->acc, (size_t)AL, ncclDouble, ncclSum, comms[g], c->stream);
+        if (r == ncclSuccess && HL > 0)
+          r = nccl().AllReduce(c->hist, c->hist, HL, ncclUint64, ncclSum, comms[g], c->stream);
+      }
+      const ncclResult_t r2 = nccl().GroupEnd();
+      if (r == ncclSuccess) r = r2;
+      if (r != ncclSuccess) {
+        g_last_cuda_error = std::string("ncclAllReduce: ") + nccl().GetErrorString(r);
+        return FMC_ERR_NCCL;
+      }
+      for (int g = 0; g < G; ++g) {
+        DeviceGuard guard_(ctxs[g]->device);
+        FMC_CUDA(cudaStreamSynchronize(ctxs[g]->stream));
+      }
+      {
+        DeviceGuard guard_(ctxs[0]->device);
+        FMC_CUDA(cudaMemcpy(acc.data(), ctxs[0]->acc, sizeof(double) * AL, cudaMemcpyDeviceToHost));
+        if (HL > 0 && counts)
+          FMC_CUDA(cudaMemcpy(counts, ctxs[0]->hist, sizeof(unsigned long long) * HL, cudaMemcpyDeviceToHost));
+      }
+      g_last_combine = FMC_COMBINE_NCCL;
+    }
+  }
+  if (g_last_combine != FMC_COMBINE_NCCL) {
+    for (int g = 0; g < G; ++g)
+      for (int i = 0; i < AL; ++i) acc[i] += accs[g][i];
+    if (HL > 0 && counts) {
+      for (size_t i = 0; i < HL; ++i) counts[i] = 0ULL;
+      for (int g = 0; g < G; ++g)
+        for (size_t i = 0; i < HL; ++i) counts[i] += hists[g][i];
+    }
+    if (G > 1) g_last_combine = FMC_COMBINE_HOST;
   }
   return fmc_decode_accumulator(model, params_start, acc.data(), sum_p, sum_p2, sum_prop, sum_prop2, nullptr,
                                 rc_count, totals);
@@ -1080,6 +1302,27 @@ int fmc_measure_dfma_peak(int device, int iters, double* tflops, float* ms_out) 
   const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
   *tflops = flops / (ms * 1e-3) / 1e12;
   if (ms_out) *ms_out = ms;
+  return FMC_OK;
+}
+
+int fmc_debug_philox4x32(const unsigned int* counters_keys, int n, unsigned int* out) {
+  if (!counters_keys || !out || n < 0) return FMC_ERR_BAD_ARG;
+  if (device_count() <= 0) return FMC_ERR_NO_DEVICE;
+  if (n == 0) return FMC_OK;
+  fmc_context* c = nullptr;
+  int rc = cached_context(0, &c);
+  if (rc != FMC_OK) return rc;
+  DeviceGuard guard_(c->device);
+  FMC_CUDA(guard_.err);
+  DevBuf in, outb;  // (double* buffers used as raw storage)
+  FMC_CUDA(cudaMalloc(&in.p, sizeof(uint32_t) * 6 * (size_t)n + 8));
+  FMC_CUDA(cudaMalloc(&outb.p, sizeof(uint32_t) * 4 * (size_t)n + 8));
+  FMC_CUDA(cudaMemcpyAsync(in.p, counters_keys, sizeof(uint32_t) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  philox_debug_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(in.p), n,
+                                                               reinterpret_cast<uint32_t*>(outb.p));
+  FMC_CUDA(cudaGetLastError());
+  FMC_CUDA(cudaMemcpyAsync(out, outb.p, sizeof(uint32_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  FMC_CUDA(cudaStreamSynchronize(c->stream));
   return FMC_OK;
 }
 

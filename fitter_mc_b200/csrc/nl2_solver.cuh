@@ -181,6 +181,12 @@ struct Nl2 {
   // far above anything the reference's own bounds (kalim = 12 / 50, mxfcal, mxiter) allow in
   // exact arithmetic, so they only bite on non-finite or inconsistent intermediate values.
   int anomaly;
+#ifdef FMC_TRACE
+  // Decision trace for tools/parity_attribution.py (host image only; the shipped kernels are never
+  // compiled with FMC_TRACE): the same record as the oracle's, after every call of assess.
+  double* trace;
+  int trace_cap, trace_len;
+#endif
 
   // ------------------------------------------------------------------ entry points
   // Per-fit reset of the state that the reference leaves to persist between fits
@@ -1347,6 +1353,24 @@ L290:
 
 L300:
   assess();
+#ifdef FMC_TRACE
+  if (trace && trace_len < trace_cap) {
+    double* t = trace + (size_t)trace_len * 10;
+    double piv = 0.0;
+    for (int q = 0; q < P; ++q) piv = piv * P + (ipivot[q] - 1);
+    t[0] = irc;
+    t[1] = sused;
+    t[2] = nfcall;
+    t[3] = niter;
+    t[4] = v[F];
+    t[5] = v[RELDX];
+    t[6] = v[RADIUS];
+    t[7] = piv;
+    t[8] = restor;
+    t[9] = v[NREDUC];
+    ++trace_len;
+  }
+#endif
   if (swtch != 0) {
     hvalid = 0;
     sused = sused + 2;

@@ -44,6 +44,7 @@ extern "C" {
 #define FMC_ERR_NO_DATA (-5)     /* fmc_launch before fmc_set_data */
 #define FMC_ERR_STATE (-6)       /* fmc_finish without a launch in flight */
 #define FMC_ERR_ALLOC (-7)       /* host or device allocation failed */
+#define FMC_ERR_NCCL (-8)        /* NCCL could not be loaded or an NCCL call failed */
 
 #define FMC_MAX_PARAM 16
 #define FMC_DEFAULT_SEED 31415ULL /* the reference's seed, utils.f90:7 */
@@ -66,8 +67,9 @@ int fmc_derived_properties(int model, const double* params, double* props);
 
 /* The Monte-Carlo loop, bootstrap.f90:297-330 (zero sums -> loop -> the caller applies
  * 328-341).  Resamples [first_counter, first_counter + nresample) are split contiguously
- * over `ngpus` devices (0 = all visible), one host thread per GPU; the per-GPU accumulators
- * are combined on the host.  Inputs: x ascending as after sort_data (bootstrap.f90:155-194),
+ * over `ngpus` devices (0 = all visible), one host thread per GPU; the per-GPU accumulator
+ * blocks are combined by ONE ncclAllReduce over NVLink (fmc_last_combine_method() == FMC_COMBINE_NCCL;
+ * replaces the OpenMP REDUCTION(+) of bootstrap.f90:310-311 across GPUs).  Inputs: x ascending as after sort_data (bootstrap.f90:155-194),
  * err_y > 0 (bootstrap.f90:134-138).
  *   sum_p[nparam], sum_p2[nparam], sum_prop[nprop], sum_prop2[nprop]  raw sums, so that the
  *       caller's lines 328-341 apply unchanged (computed from compensated shifted sums).
@@ -89,11 +91,35 @@ int fmc_bootstrap_run(int model, int ndata, const double* x, const double* y, co
 int fmc_fit_once(int model, int ndata, const double* x, const double* y, const double* err_y,
                  double* params, int* rc2);
 
+/* Test hook: the raw output words of the device's counter-based generator (Philox4x32-10, rng.cuh).
+ * counters_keys[n][6] = counter words c0..c3 then key words k0, k1; out[n][4].  Lets the published
+ * known-answer vectors be checked on the GPU itself. */
+int fmc_debug_philox4x32(const unsigned int* counters_keys, int n, unsigned int* out);
+
 /* The Gaussian offsets (in units of err_y) the engine uses for resamples
  * [first_counter, first_counter+nresample): z_out[nresample][ndata].  Replaces
  * `rang(ndata, offset)` (utils.f90:345-364) as a reproducible per-sample generator. */
 int fmc_generate_offsets(unsigned long long seed, long long first_counter, long long nresample,
                          int ndata, double* z_out);
+
+/* How the last fmc_bootstrap_run / fmc_bootstrap_run_binned call combined its GPUs' accumulators. */
+#define FMC_COMBINE_NONE 0 /* one GPU: nothing to combine */
+#define FMC_COMBINE_NCCL 1 /* one ncclAllReduce(sum, double) over the GPUs' streams */
+#define FMC_COMBINE_HOST 2 /* NCCL not loadable on this host: blocks added on the host */
+int fmc_last_combine_method(void);
+
+/* ---------------------------------------------------------------- NCCL combine, one rank per GPU
+ * For callers that run one process (or thread) per GPU -- bench.py under torchrun, an MPI build of the
+ * Fortran driver: rank 0 obtains an id, the caller broadcasts its 128 bytes by its own means
+ * (MPI_Bcast, torch.distributed), every rank binds its context, and after each fmc_launch one
+ * fmc_allreduce enqueues the single ncclAllReduce of the accumulator block (and of the binned counts,
+ * when enabled) on the context's stream.  NCCL (libnccl.so.2) is loaded at run time.
+ *   fmc_nccl_available   0 = not loadable, else NCCL's version code (or 1).
+ *   fmc_allreduce        no-op for a context that was never bound or is the only rank. */
+int fmc_nccl_available(void);
+int fmc_nccl_unique_id(char* id128);
+int fmc_nccl_init_rank(fmc_context* ctx, const char* id128, int nranks, int rank);
+int fmc_allreduce(fmc_context* ctx);
 
 /* ---------------------------------------------------------------- context API (one GPU)
  * For callers that keep data resident, overlap transfers, shard over ranks or combine
@@ -109,6 +135,9 @@ int fmc_set_data(fmc_context* ctx, int model, int ndata, const double* x, const 
  * torch tensor that is then all-reduced with NCCL).  NULL = the context's own buffer. */
 int fmc_set_accumulator_dev(fmc_context* ctx, double* acc_dev);
 int fmc_accumulator_len(const fmc_context* ctx);
+/* Copy the accumulator block (after the work queued on the context's stream, e.g. fmc_launch and
+ * fmc_allreduce) to the host; decode it with fmc_decode_accumulator. */
+int fmc_get_accumulator(fmc_context* ctx, double* acc_host);
 /* Enqueue: zero the accumulator, run the fit kernel for `nresample` resamples.  Asynchronous.
  * z_inject_dev: NULL or DEVICE pointer [nresample][ndata].  keep_per_resample != 0 keeps
  * per-resample params/props/counters on the device for fmc_finish. */
@@ -199,6 +228,9 @@ int fmc_bootstrap_run_binned(int model, int ndata, const double* x, const double
 
 /* Device time of the last fit kernel (CUDA events on the launching stream), milliseconds. */
 float fmc_last_kernel_ms(fmc_context* ctx);
+/* Number of this library's kernels the last fmc_launch enqueued (jac0, init_shared/init_pass, iterate,
+ * warp_fit, hist -- per chunk of 2^21 resamples). */
+long long fmc_last_launch_count(const fmc_context* ctx);
 /* Grid geometry chosen for the last launch: blocks, threads per block, blocks per SM, SMs. */
 int fmc_last_launch_geometry(const fmc_context* ctx, int* out4);
 

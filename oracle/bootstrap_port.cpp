@@ -158,7 +158,8 @@ struct Workspace {
   Workspace(int n, int p) : iv(nl2::iv_len(p)), v(nl2::v_len(n, p)) {}
 };
 
-void fit_data(FitCtx& ctx, int n, int p, double* params, int flags, Workspace& ws, int* counters) {
+void fit_data(FitCtx& ctx, int n, int p, double* params, int flags, Workspace& ws, int* counters,
+              double* trace = nullptr, int trace_cap = 0, int* trace_len = nullptr) {
   nl2::Options opt;
   opt.copy_jac = (flags & FMC_ORACLE_COPY_JAC) != 0;
   int ix_local = 2;
@@ -173,6 +174,12 @@ void fit_data(FitCtx& ctx, int n, int p, double* params, int flags, Workspace& w
       // parameters are unchanged because covclc restores x and r exactly.
       iv[14 - 1] = 0;
       iv[15 - 1] = 0;
+    }
+    if (trace) {  // one trace per nl2sno call
+      opt.trace = trace + (size_t)pass * trace_cap * nl2::TRACE_W;
+      opt.trace_cap = trace_cap;
+      opt.trace_len = trace_len + pass;
+      trace_len[pass] = 0;
     }
     if (flags & FMC_ORACLE_ANALYTIC_JAC)
       nl2::nl2sol(n, p, params, madr, madj, iv, v, &ctx, opt);
@@ -248,6 +255,19 @@ int fmc_oracle_fit_data(int model, int n, const double* x, const double* y_fit, 
   FitCtx ctx{model, x, y_fit, rerr.data(), 0};
   Workspace ws(n, p);
   fit_data(ctx, n, p, params, flags, ws, counters);
+  return 0;
+}
+
+int fmc_oracle_fit_trace(int model, int n, const double* x, const double* y_fit, const double* err,
+                         double* params, int flags, int* counters, double* trace, int trace_cap, int* trace_len) {
+  if (model < 0 || model >= kNumModels) return -1;
+  const int p = kModels[model].nparam;
+  if (n < p || !trace || !trace_len || trace_cap < 1) return -2;
+  std::vector<double> rerr(n);
+  for (int i = 0; i < n; ++i) rerr[i] = 1.0 / err[i];
+  FitCtx ctx{model, x, y_fit, rerr.data(), 0};
+  Workspace ws(n, p);
+  fit_data(ctx, n, p, params, flags, ws, counters, trace, trace_cap, trace_len);
   return 0;
 }
 

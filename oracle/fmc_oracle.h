@@ -51,6 +51,12 @@ void fmc_oracle_derived_properties(int model, const double* params, double* prop
 int fmc_oracle_fit_data(int model, int n, const double* x, const double* y_fit, const double* err,
                         double* params, int flags, int* counters /* [2][6] or NULL */);
 
+/* The same with a decision trace (tools/parity_attribution.py): after every call of assess
+ * (toms573.f90:1191) one record of 10 doubles -- iv(irc), model used, nfcall, niter, f, reldx, radius,
+ * pivot order, stppar, nreduc -- into trace[pass][trace_cap][10]; trace_len[2] = records per call. */
+int fmc_oracle_fit_trace(int model, int n, const double* x, const double* y_fit, const double* err,
+                         double* params, int flags, int* counters, double* trace, int trace_cap, int* trace_len);
+
 /* residual vector madr (bootstrap.f90:229-250) and chi^2 (bootstrap.f90:452-458) */
 void fmc_oracle_madr(int model, int n, const double* x, const double* y_fit, const double* err,
                      const double* params, double* r);

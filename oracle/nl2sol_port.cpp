@@ -1889,6 +1889,22 @@ L300:
   lstgst = IV(STLSTG);
   x01 = IV(X0);
   assess(d_, iv, p, &V(step1), &V(lstgst), v, x, &V(x01));
+  if (opt.trace && opt.trace_len && *opt.trace_len < opt.trace_cap) {
+    double* t = opt.trace + (size_t)(*opt.trace_len) * TRACE_W;
+    double piv = 0.0;
+    for (int q = 0; q < p; ++q) piv = piv * p + ((&IV(IPIVOT))[q] - 1);
+    t[0] = IV(IRC);
+    t[1] = IV(SUSED);
+    t[2] = IV(NFCALL);
+    t[3] = IV(NITER);
+    t[4] = V(V_F);
+    t[5] = V(RELDX);
+    t[6] = V(RADIUS);
+    t[7] = piv;
+    t[8] = IV(RESTOR);
+    t[9] = V(NREDUC);
+    ++*opt.trace_len;
+  }
   if (IV(SWITCH) == 0) goto L310;
   IV(IV_H) = -std::abs(IV(IV_H));
   IV(SUSED) = IV(SUSED) + 2;

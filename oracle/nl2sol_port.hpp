@@ -30,7 +30,14 @@ struct Options {
   bool covariance = true;   // covclc pass at convergence (dead work in the reference, toms573.f90:1400-1418)
   bool copy_jac = true;     // allocate/copy j(nn,p) on each nl2itr call (toms573.f90:876-884, 1434-1442)
   int* lsvmin_ix = nullptr; // LCG state of lsvmin (SAVEd `ix`, toms573.f90:3974); nullptr -> process-global
+  // Decision trace (tools/parity_attribution.py): one record of TRACE_W doubles after every call of
+  // assess (toms573.f90:1191): iv(irc), model used for the step, nfcall, niter, f at the trial point,
+  // reldx, radius, pivot order of the current QR factorisation (digits base p), iv(restor), nreduc.
+  double* trace = nullptr;
+  int trace_cap = 0;        // records
+  int* trace_len = nullptr;
 };
+enum { TRACE_W = 10 };
 
 // IV / V lengths as allocated at bootstrap.f90:273.
 inline int iv_len(int p) { return p + 60; }

@@ -93,6 +93,42 @@ int fit_one(int n, const double* x, const double* yfit, const double* err, doubl
   return 0;
 }
 
+#ifdef FMC_TRACE
+// fit_one with the solver's decision trace (tools/parity_attribution.py): trace[pass][cap][10]
+template <class M, int JAC = JAC_FD>
+int fit_one_trace(int n, const double* x, const double* yfit, const double* err, double* params, int* counters,
+                  double* trace, int cap, int* len) {
+  constexpr int P = M::NPARAM;
+  std::vector<double> rerr(n);
+  for (int i = 0; i < n; ++i) rerr[i] = 1.0 / err[i];
+  Nl2<P> s;
+  std::memset(&s, 0, sizeof(s));
+  s.reset_fit();
+  for (int pass = 0; pass < 2; ++pass) {
+    s.begin(params);
+    s.trace = trace + (size_t)pass * cap * 10;
+    s.trace_cap = cap;
+    s.trace_len = 0;
+    int npass = 0;
+    for (;;) {
+      run_pass<M, JAC>(s, n, x, yfit, rerr.data());
+      ++npass;
+      if (!s.resume()) break;
+      if (npass > 2 * (k::mxfcal + k::mxiter)) break;
+    }
+    len[pass] = s.trace_len;
+    for (int i = 0; i < P; ++i) params[i] = s.x[i];
+    int* c = counters + 5 * pass;
+    c[0] = s.rc;
+    c[1] = s.nfcall;
+    c[2] = s.ngcall;
+    c[3] = s.niter;
+    c[4] = npass;
+  }
+  return 0;
+}
+#endif
+
 template <class M, int JAC = JAC_FD>
 int bootstrap(int n, const double* x, const double* y, const double* err, const double* start,
               long long nres, const double* z, unsigned long long seed, long long first,
@@ -507,6 +543,24 @@ int emul_bootstrap_trial1(int model, int n, const double* x, const double* y, co
   }
   return -1;
 }
+
+#ifdef FMC_TRACE
+int emul_fit_trace(int model, int jac, int n, const double* x, const double* yfit, const double* err, double* params,
+                   int* counters, double* trace, int cap, int* len) {
+#define TRACE_CASE(ID, M)                                                                               \
+  case ID:                                                                                              \
+    return jac ? fit_one_trace<M, JAC_ANALYTIC>(n, x, yfit, err, params, counters, trace, cap, len)     \
+               : fit_one_trace<M, JAC_FD>(n, x, yfit, err, params, counters, trace, cap, len);
+  switch (model) {
+    TRACE_CASE(0, ModelUser)
+    TRACE_CASE(1, ModelTest4)
+    TRACE_CASE(2, ModelPeaks10)
+    TRACE_CASE(3, ModelStiff4)
+  }
+#undef TRACE_CASE
+  return -1;
+}
+#endif
 
 int emul_row_grad(int model, const double* x, double xi, double* grad) {
   switch (model) {
