@@ -104,7 +104,7 @@ FMC_HD FMC_INLINE double exp_fast(double x) {
 }
 
 FMC_HD FMC_INLINE double exp(double x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) || defined(FMC_HOST_EXP_FAST)  // (the latter: host images that mimic the device)
   return exp_fast(x);
 #else
   return ::exp(x);

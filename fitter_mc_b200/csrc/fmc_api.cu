@@ -730,19 +730,20 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   const int jac = c->jac;
   if (jac == fmc::JAC_ANALYTIC && !m.analytic) return FMC_ERR_BAD_ARG;  // double-only model_y, no model_grad
   const bool per_warp = c->mapping == FMC_FIT_PER_WARP;
-  const fmc::WarpEntry wentry = per_warp ? fmc::fmc_warp_entry(c->model) : fmc::WarpEntry{nullptr, nullptr};
+  const fmc::WarpEntry wentry = per_warp ? fmc::fmc_warp_entry(c->model) : fmc::WarpEntry{nullptr, nullptr, 0};
   fmc::WarpArgs wa;
   std::memset(&wa, 0, sizeof(wa));
   if (per_warp) {
     if (!wentry.launch) return FMC_ERR_BAD_MODEL;
     // columns staged in shared memory: all four when they fit, else x and 1/err, else none
     const size_t col = sizeof(double) * (size_t)c->n_w;
-    wa.stage = (4 + m.naux) * col + 1024 <= (size_t)c->max_smem_optin
+    const size_t fixed = wentry.solver_smem + 1024;  // the warps' solver states + static shared memory
+    wa.stage = (4 + m.naux) * col + fixed <= (size_t)c->max_smem_optin
                    ? 4
-                   : ((2 + m.naux) * col + 1024 <= (size_t)c->max_smem_optin ? 2 : 0);
+                   : ((2 + m.naux) * col + fixed <= (size_t)c->max_smem_optin ? 2 : 0);
     wa.cols = c->cols_dev;
     wa.n_w = c->n_w;
-    shmem = wa.stage > 0 ? (wa.stage + m.naux) * col : 0;
+    shmem = wentry.solver_smem + (wa.stage > 0 ? (wa.stage + m.naux) * col : 0);
     FMC_CUDA(wentry.occupancy(inject, jac, shmem, &bps));
   } else {
     FMC_CUDA(m.occupancy(inject, smem, jac, shmem, &bps));

@@ -21,11 +21,13 @@
 //    stored t_i (p sums).  Neither sweep holds the sums and the point-dependent constants of the
 //    other, which is what keeps the loops inside the register file; the FP64 work is the same as
 //    in one sweep.
-//  * the per-lane partial sums are combined by a butterfly of warp shuffles, which leaves the
-//    bitwise SAME totals in every lane; every lane then runs the (cheap, p x p) solver step on
-//    those totals redundantly: identical inputs, identical control flow, no divergence, and no
-//    lane ever waits for another fit.  Both nl2sno calls of fit_data and their initial passes run
-//    inside the one kernel; warps take the next resample from a shared counter.
+//  * the per-lane partial sums are combined by a butterfly of warp shuffles; lane 0 hands the totals
+//    to the solver, whose state (4.4 KB at p = 10) lives in SHARED memory, one copy per warp, and
+//    runs the p x p solver step alone (an instruction issued for one lane costs what it costs for
+//    32); the other lanes then read the next evaluation point from shared memory by broadcast.  No
+//    divergence between fits, and no lane ever waits for another fit.  Both nl2sno calls of
+//    fit_data and their initial passes run inside the one kernel; warps take the next resample
+//    from a shared counter.
 //
 // The deviates are the same function of (seed, resample, data point) as in the per-thread
 // kernels, so both mappings fit the same resampled data sets; sums are formed in a different
@@ -155,6 +157,12 @@ FMC_INLINE __device__ void sweep_b(const WarpCols& c, int n_w, int lane, const P
   for (int i = 0; i < P; ++i) lky[i] = warp_allsum(lky[i]);
 }
 
+// Shared memory of one warp's solver state (16-byte granules).
+template <int P>
+FMC_HD constexpr size_t warp_solver_bytes() {
+  return (sizeof(Nl2<P>) + 15) / 16 * 16;
+}
+
 // Arguments of the warp kernel beyond KernelArgs.
 struct WarpArgs {
   const double* cols;   // [4 + NAUX][n_w] lane-major x, y, err, 1/err, auxiliary values (global)
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
   WarpCols c;
   {
     // staged columns: x and 1/err first (both sweeps / the sums need them most), then y and err
-    double* sm = reinterpret_cast<double*>(smem_raw);
+    double* sm = reinterpret_cast<double*>(smem_raw + (FMC_WARP_THREADS / 32) * warp_solver_bytes<P>());
     const double* gx = wa.cols;
     const double* gy = wa.cols + n_w;
     const double* ge = wa.cols + 2 * (size_t)n_w;
@@ -213,9 +221,14 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  double* tbuf = wa.tscratch + ((size_t)blockIdx.x * (FMC_WARP_THREADS / 32) + (threadIdx.x >> 5)) * (size_t)n_w;
+  const int warp = threadIdx.x >> 5;
+  double* tbuf = wa.tscratch + ((size_t)blockIdx.x * (FMC_WARP_THREADS / 32) + warp) * (size_t)n_w;
 
-  Nl2<P> s;
+  // The solver state of the warp's fit lives in SHARED memory and lane 0 alone runs the solver step
+  // between passes (an instruction issued for one lane costs what it costs for 32): one copy per fit
+  // instead of 32 thread-local ones (4.4 KB each at p = 10 -- 1.1 MB per SM, i.e. every access an L2
+  // round trip), and the other lanes read the next evaluation point from it by broadcast.
+  Nl2<P>& s = *reinterpret_cast<Nl2<P>*>(smem_raw + (size_t)warp * warp_solver_bytes<P>());
   double msum[NM], mcmp[NM];  // lane 0 of each warp carries the warp's moment sums
 #pragma unroll
   for (int i = 0; i < NM; ++i) {
@@ -226,33 +239,34 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
   M::derived_properties(a.start, cq);
   unsigned int n_fit = 0, n_fcall = 0, n_gcall = 0, n_iter = 0, n_pass = 0;
 
-  // one pass at s.x (and, WITH_B, the J(x0)^T r(x) part), results into the solver
+  // one pass at s.x (and, WITH_B, the J(x0)^T r(x) part); lane 0 hands the totals to the solver
   auto pass = [&](auto with_b, unsigned long long id, const double* zrow) {
     constexpr bool WITH_B = decltype(with_b)::value;
     double h1[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) h1[i] = JAC == JAC_ANALYTIC ? 1.0 : s.hA[i];
     {
       PassPoint<P> pa;
+#pragma unroll
+      for (int i = 0; i < P; ++i) h1[i] = JAC == JAC_ANALYTIC ? 1.0 : s.hA[i];
       pa.set(s.x, h1);
       SweepA<P> acc;
       acc.zero();
       sweep_a<M, INJECT, WITH_B, JAC>(c, a.n, n_w, lane, a.seed, id, zrow, pa, tbuf, acc);
       acc.allsum();
-      s.res_f = acc.f;
+      if (lane == 0) {
+        s.res_f = acc.f;
 #pragma unroll
-      for (int i = 0; i < P; ++i) s.res_g[i] = JAC == JAC_ANALYTIC ? acc.g[i] : acc.g[i] * (1.0 / h1[i]);
-      int q = 0;
+        for (int i = 0; i < P; ++i) s.res_g[i] = JAC == JAC_ANALYTIC ? acc.g[i] : acc.g[i] * (1.0 / h1[i]);
+        int q = 0;
 #pragma unroll
-      for (int i = 0; i < P; ++i)
+        for (int i = 0; i < P; ++i)
 #pragma unroll
-        for (int jj = 0; jj <= i; ++jj) {
-          s.res_G[q] = JAC == JAC_ANALYTIC ? acc.G[q] : acc.G[q] * ((1.0 / h1[i]) * (1.0 / h1[jj]));
-          ++q;
-        }
+          for (int jj = 0; jj <= i; ++jj) {
+            s.res_G[q] = JAC == JAC_ANALYTIC ? acc.G[q] : acc.G[q] * ((1.0 / h1[i]) * (1.0 / h1[jj]));
+            ++q;
+          }
+      }
     }
     if constexpr (WITH_B) {
-      __syncwarp();  // the t_i of this warp's other lanes are not read, but keep the sweeps ordered
       double hb[P];
 #pragma unroll
       for (int i = 0; i < P; ++i) hb[i] = JAC == JAC_ANALYTIC ? 1.0 : s.hJ[i];
@@ -260,9 +274,25 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
       pb.set(s.x0, hb);
       double lky[P];
       sweep_b<M, JAC>(c, n_w, lane, pb, tbuf, lky);
+      if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < P; ++i) s.res_lky[i] = JAC == JAC_ANALYTIC ? lky[i] : lky[i] * (1.0 / hb[i]);
+        for (int i = 0; i < P; ++i) s.res_lky[i] = JAC == JAC_ANALYTIC ? lky[i] : lky[i] * (1.0 / hb[i]);
+      }
     }
+  };
+  // the solver step: lane 0 consumes the pass; everybody learns whether another pass is wanted
+  auto step = [&](int& passes) -> bool {
+    int more = 0;
+    if (lane == 0) {
+      more = s.resume() ? 1 : 0;
+      if (more && passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
+        s.anomaly |= 8;
+        s.rc = 9;
+        more = 0;
+      }
+    }
+    more = __shfl_sync(0xffffffffu, more, 0);  // (also orders lane 0's writes before the others' reads)
+    return more != 0;
   };
 
   for (;;) {
@@ -274,45 +304,50 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
     const unsigned long long id = (unsigned long long)(a.first + slot);
     const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
 
-    s.reset_fit();
-    double xs[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) xs[i] = a.start[i];
-    int cnt[10];
+    int cnt[10];  // (lane 0's copy is the one that is used)
     for (int call = 0; call < 2; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
-      s.begin(xs);
+      if (lane == 0) {
+        if (call == 0) {
+          s.reset_fit();
+          s.begin(a.start);
+        } else {
+          double xs[P];
+#pragma unroll
+          for (int i = 0; i < P; ++i) xs[i] = s.x[i];
+          s.begin(xs);
+        }
+      }
+      __syncwarp();
       int passes = 1;
       // first evaluation of the call: residual + Jacobian at the starting point, D = 1
       pass(std::false_type{}, id, zrow);
-      bool more = s.resume();
+      bool more = step(passes);
       while (more) {
         pass(std::true_type{}, id, zrow);
         ++passes;
-        more = s.resume();
-        if (more && passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
-          s.anomaly |= 8;
-          s.rc = 9;
-          more = false;
-        }
+        more = step(passes);
       }
-      cnt[5 * call + 0] = s.rc;
-      cnt[5 * call + 1] = s.nfcall;
-      cnt[5 * call + 2] = s.ngcall;
-      cnt[5 * call + 3] = s.niter;
-      cnt[5 * call + 4] = passes;
-      if (s.anomaly != 0 && a.anom != nullptr && lane == 0) {  // same record format as iterate_kernel
-        const unsigned long long na = atomicAdd(a.anom, 1ULL);
-        if (na < (unsigned long long)ANOM_CAP) {
-          a.anom[1 + 2 * na] = id;
-          a.anom[2 + 2 * na] = (unsigned long long)(s.anomaly | (call << 8));
+      if (lane == 0) {
+        cnt[5 * call + 0] = s.rc;
+        cnt[5 * call + 1] = s.nfcall;
+        cnt[5 * call + 2] = s.ngcall;
+        cnt[5 * call + 3] = s.niter;
+        cnt[5 * call + 4] = passes;
+        if (s.anomaly != 0 && a.anom != nullptr) {  // same record format as iterate_kernel
+          const unsigned long long na = atomicAdd(a.anom, 1ULL);
+          if (na < (unsigned long long)ANOM_CAP) {
+            a.anom[1 + 2 * na] = id;
+            a.anom[2 + 2 * na] = (unsigned long long)(s.anomaly | (call << 8));
+          }
         }
+        s.anomaly = 0;
       }
-      s.anomaly = 0;
-#pragma unroll
-      for (int i = 0; i < P; ++i) xs[i] = s.x[i];
     }
 
-    if (lane == 0) {  // every lane holds the same result; one of them records it
+    if (lane == 0) {  // one lane records the fit
+      double xs[P];
+#pragma unroll
+      for (int i = 0; i < P; ++i) xs[i] = s.x[i];
       double props[Q > 0 ? Q : 1];
       M::derived_properties(xs, props);  // bootstrap.f90:316
 #pragma unroll
@@ -340,6 +375,7 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
       if (a.counters_out)
         for (int i = 0; i < 10; ++i) a.counters_out[slot * 10 + i] = cnt[i];
     }
+    __syncwarp();
   }
 
   // ---- epilogue: block reduction of the per-warp sums (lanes other than 0 contribute zero)
@@ -373,6 +409,7 @@ struct WarpEntry {
   cudaError_t (*launch)(const KernelArgs&, const WarpArgs&, bool inject, int jac, int grid, size_t shmem,
                         cudaStream_t);
   cudaError_t (*occupancy)(bool inject, int jac, size_t shmem, int* blocks_per_sm);
+  size_t solver_smem;  // shared memory for the per-warp solver states of one block
 };
 
 template <class M>
@@ -406,7 +443,9 @@ struct WarpBinding {
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, kern, FMC_WARP_THREADS, shmem);
     });
   }
-  static WarpEntry entry() { return WarpEntry{launch, occupancy}; }
+  static WarpEntry entry() {
+    return WarpEntry{launch, occupancy, (FMC_WARP_THREADS / 32) * warp_solver_bytes<M::NPARAM>()};
+  }
 };
 
 // kernels_warp.cu, one object per model
@@ -421,7 +460,7 @@ inline WarpEntry fmc_warp_entry(int model) {
     case 2: return fmc_warp_entry_model2();
     case 3: return fmc_warp_entry_model3();
   }
-  return WarpEntry{nullptr, nullptr};
+  return WarpEntry{nullptr, nullptr, 0};
 }
 
 }  // namespace fmc

@@ -162,6 +162,7 @@ void fit_data(FitCtx& ctx, int n, int p, double* params, int flags, Workspace& w
               double* trace = nullptr, int trace_cap = 0, int* trace_len = nullptr) {
   nl2::Options opt;
   opt.copy_jac = (flags & FMC_ORACLE_COPY_JAC) != 0;
+  opt.gqt_retry_cap = (flags & FMC_ORACLE_SAFETY_CAP) ? 1000 : 0;
   int ix_local = 2;
   opt.lsvmin_ix = (flags & FMC_ORACLE_LSVMIN_PER_FIT) ? &ix_local : nullptr;
   int* iv = ws.iv.data();

@@ -42,6 +42,9 @@ void fmc_oracle_derived_properties(int model, const double* params, double* prop
 #define FMC_ORACLE_LSVMIN_PER_FIT 4 /* reset lsvmin's LCG to 2 at the start of each fit (order-independent results) */
 #define FMC_ORACLE_HISTOGRAM 8    /* write props to /dev/null-like text sink under a critical section (cost model of bootstrap.f90:319-325) */
 
+#define FMC_ORACLE_SAFETY_CAP 32  /* bound gqtstp's retry loop at 1000 rounds (the reference's is unbounded and can spin
+                                     forever on ill-conditioned fits -- tests/test_robustness.py); for checks on the C5
+                                     stress data, where a hung checker would hang the test-suite */
 #define FMC_ORACLE_ANALYTIC_JAC 16 /* fit with nl2sol + an analytic madj instead of nl2sno (README:35-42) */
 
 /* counters[pass][k]: k = 0 iv(1) return code, 1 nfcall, 2 ngcall, 3 niter, 4 nfcov, 5 ngcov */

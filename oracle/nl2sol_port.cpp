@@ -781,8 +781,16 @@ L390:
 }
 
 // toms573.f90:2471-3039 -- Goldfeld-Quandt-Trotter step for the augmented model.
+// Optional guard for the checker (Options::gqt_retry_cap): the retry after a failed factorisation at
+// label 200 has no iteration limit in the reference (toms573.f90:2790-2812) and is a latent
+// non-termination (tests/test_robustness.py).  0 = the reference's behaviour.  When the cap is hit the
+// last solved step is kept, as the product does (nl2_solver.cuh, anomaly bit 2).
+thread_local int t_gqt_retry_cap = 0;
+
 void gqtstp(const double* d_, const double* dig_, double* dihdi_, int* ka_, double* l_, int p,
             double* step_, double* v, double* w_, int* lsvmin_ix) {
+  int n_retry = 0;
+  bool have_q = false;
   const double* d = d_ - 1;
   const double* dig = dig_ - 1;
   double* dihdi = dihdi_ - 1;
@@ -869,6 +877,7 @@ L50:
   livmul(p, &w[q], l_, dig_);
   V(NREDUC) = half * dotprd(p, &w[q], &w[q]);
   litvmu(p, &w[q], l_, &w[q]);
+  have_q = true;
   dst = v2norm(p, &w[q]);
   V(DST0) = dst;
   phi = dst - rad;
@@ -969,6 +978,10 @@ L60:
   lk = std::fmax(lk, phi * w[phipin]);
 
 L200:
+  if (t_gqt_retry_cap > 0 && ++n_retry > t_gqt_retry_cap) {
+    if (have_q) goto L270;
+    goto L430;
+  }
   ka = ka + 1;
   if (-V(DST0) >= alphak || alphak < lk || alphak >= uk)
     alphak = uk * std::fmax(p001, std::sqrt(lk / uk));
@@ -994,6 +1007,7 @@ L200:
 L230:
   livmul(p, &w[q], l_, dig_);
   litvmu(p, &w[q], l_, &w[q]);
+  have_q = true;
   dst = v2norm(p, &w[q]);
   phi = dst - rad;
   if (phi <= phimax && phi >= phimin) goto L270;
@@ -2118,6 +2132,7 @@ void nl2itr(double* d, int* iv, double* jac, int n, int nn, int p, double* r, do
 // toms573.f90:590-769 -- forward-difference Jacobian + reverse-communication loop.
 void nl2sno(int n, int p, double* x, calcr_fn calcr, int* iv, double* v, void* ctx,
             const Options& opt) {
+  t_gqt_retry_cap = opt.gqt_retry_cap;
   const double hfac = 1e3, negpt5 = -0.5, one = 1.0, zero = 0.0;
   bool strted;
   int dk, d1, i, j1, j1k, k, nf, rn, r1;
@@ -2191,6 +2206,7 @@ L100:
 // with the finite-difference block replaced by one call of the user's calcj.
 void nl2sol(int n, int p, double* x, calcr_fn calcr, calcj_fn calcj, int* iv, double* v, void* ctx,
             const Options& opt) {
+  t_gqt_retry_cap = opt.gqt_retry_cap;
   bool strted;
   int d1, j1, nf, r1;
 

@@ -29,6 +29,7 @@ typedef void (*calcr_fn)(int n, int p, const double* x, int* nf, double* r, void
 struct Options {
   bool covariance = true;   // covclc pass at convergence (dead work in the reference, toms573.f90:1400-1418)
   bool copy_jac = true;     // allocate/copy j(nn,p) on each nl2itr call (toms573.f90:876-884, 1434-1442)
+  int gqt_retry_cap = 0;    // > 0: bound gqtstp's retry loop (unbounded in the reference: a latent non-termination)
   int* lsvmin_ix = nullptr; // LCG state of lsvmin (SAVEd `ix`, toms573.f90:3974); nullptr -> process-global
   // Decision trace (tools/parity_attribution.py): one record of TRACE_W doubles after every call of
   // assess (toms573.f90:1191): iv(irc), model used for the step, nfcall, niter, f at the trial point,

@@ -72,6 +72,13 @@ def c4(n=10000):
 # (tests/test_c5_stress.py).  "c5mild" is the untuned recipe, used where per-fit parameter
 # parity is asserted.
 C5_REL, C5_FLOOR = 13.0, 1.0
+# The fit to the un-resampled C5 data (bootstrap.f90:288-291) as the oracle returns it in the build
+# container, from params_init = (1, 1, 1, 1): 42 evaluations into the degenerate basin.  That path is
+# chaotic (other libm builds of exp/log send it elsewhere, and the reference's gqtstp can spin forever
+# on it -- tests/test_robustness.py), so every test and bench of C5 starts its resamples from these
+# committed values instead of refitting.
+C5_FITTED = np.array([float.fromhex("-0x1.0cbd778212d33p+13"), float.fromhex("0x1.6c15b0c6968e6p+5"),
+                      float.fromhex("0x1.fb0bea4540d5ep-2"), float.fromhex("0x1.c90048cca64bap-1")])
 
 
 def c5(n=1000, rel=C5_REL, floor=C5_FLOOR):

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "libfmc_oracle.so")
 
-COVARIANCE, COPY_JAC, LSVMIN_PER_FIT, HISTOGRAM, ANALYTIC_JAC = 1, 2, 4, 8, 16
+COVARIANCE, COPY_JAC, LSVMIN_PER_FIT, HISTOGRAM, ANALYTIC_JAC, SAFETY_CAP = 1, 2, 4, 8, 16, 32
 RNG_RANLUX, RNG_INJECT = 0, 1
 NCOUNTERS = 6
 

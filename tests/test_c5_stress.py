@@ -41,10 +41,14 @@ def _chi2(x, y, err, z, p):
 
 def _setup(oracle, nres, seed=1):
     model, x, y, err = datasets.dataset("c5")
-    info = oracle.model_info(model)
-    start, _ = oracle.fit_data(model, x, y, err, info["params_init"])
+    start = datasets.C5_FITTED.copy()     # committed: the initial fit itself is chaotic (tests/datasets.py)
     z = np.random.default_rng(seed).normal(size=(nres, len(x)))
     return model, x, y, err, start, z
+
+
+def _oracle_flags(oracle):
+    # the checker must not hang the suite on this data: bound the reference's unbounded gqtstp retry loop
+    return oracle.LSVMIN_PER_FIT | oracle.SAFETY_CAP
 
 
 def _chi2_gates(name, x, y, err, z, got, want, rc_got):
@@ -66,12 +70,15 @@ def _chi2_gates(name, x, y, err, z, got, want, rc_got):
 
 def test_c5_recipe_gives_a_high_non_convergence_rate(oracle):
     model, x, y, err, start, z = _setup(oracle, 1000)
-    res = oracle.bootstrap(model, x, y, err, start, len(z), z=z, nthreads=8)
+    res = oracle.bootstrap(model, x, y, err, start, len(z), z=z, flags=_oracle_flags(oracle), nthreads=8)
     rc = res["rc_count"]
     frac = rc[7:11].sum() / len(z)
     print("\n[c5 stress] oracle return codes 3..10: %s  -> %.1f %% codes 7-10" % (rc[3:11].tolist(), 100 * frac))
     assert rc.sum() == len(z)
     assert frac >= NONCONV_MIN
+    # the committed start is what the oracle's initial fit gives in the build container
+    refit, _ = oracle.fit_data(model, x, y, err, oracle.model_info(model)["params_init"], flags=_oracle_flags(oracle))
+    print("[c5 stress] initial fit here: %s ; committed: %s" % (refit.tolist(), start.tolist()))
     # the untuned recipe has none (which is why the noise was tuned up)
     model, x, y, err = datasets.dataset("c5mild")
     start, _ = oracle.fit_data(model, x, y, err, oracle.model_info(model)["params_init"])
@@ -81,8 +88,7 @@ def test_c5_recipe_gives_a_high_non_convergence_rate(oracle):
 
 def test_host_image_of_the_solver_reaches_the_oracles_chi2_on_c5(emul, oracle):
     model, x, y, err, start, z = _setup(oracle, 240)
-    flags = oracle.LSVMIN_PER_FIT
-    want = oracle.bootstrap(model, x, y, err, start, len(z), z=z, flags=flags, nthreads=8)
+    want = oracle.bootstrap(model, x, y, err, start, len(z), z=z, flags=_oracle_flags(oracle), nthreads=8)
     got, _, cnt, anomalies = _emul_run(emul, model, 0, x, y, err, start, z, 4, 2)
     rc = cnt[:, 1, 0]
     _chi2_gates("host image", x, y, err, z, got, want["params"], rc)
@@ -97,7 +103,7 @@ def test_cuda_path_reaches_the_oracles_chi2_on_c5(oracle, mapping):
     import fitter_mc_b200 as fmc
 
     model, x, y, err, start, z = _setup(oracle, 1000)
-    want = oracle.bootstrap(model, x, y, err, start, len(z), z=z, flags=oracle.LSVMIN_PER_FIT, nthreads=8)
+    want = oracle.bootstrap(model, x, y, err, start, len(z), z=z, flags=_oracle_flags(oracle), nthreads=8)
     zdev = None
     ctx = fmc.Context(0)
     try:
@@ -141,7 +147,7 @@ def test_c5_ensemble_matches_the_reference_stream(oracle):
     import fitter_mc_b200 as fmc
 
     model, x, y, err = datasets.dataset("c5")
-    start, _ = oracle.fit_data(model, x, y, err, oracle.model_info(model)["params_init"])
+    start = datasets.C5_FITTED.copy()
     na, nb = 20000, 4000
     ctx = fmc.Context(0)
     try:
@@ -151,7 +157,7 @@ def test_c5_ensemble_matches_the_reference_stream(oracle):
     finally:
         ctx.close()
     oracle.initialise_rng()
-    ref = oracle.bootstrap(model, x, y, err, start, nb, nthreads=8)
+    ref = oracle.bootstrap(model, x, y, err, start, nb, flags=_oracle_flags(oracle), nthreads=8)
     fa = got["rc_count"][7:11].sum() / na
     fb = ref["rc_count"][7:11].sum() / nb
     se = np.sqrt(fa * (1 - fa) / na + fb * (1 - fb) / nb)

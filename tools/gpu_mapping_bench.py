@@ -31,7 +31,10 @@ def main():
     for name in names:
         model, x, y, err = datasets.dataset(name)
         info = fmc.initialise_model(model)
-        start, _ = oracle.fit_data(model, x, y, err, info["params_init"])
+        if name == "c5":   # committed start: the initial fit of the stress data is chaotic (tests/datasets.py)
+            start = datasets.C5_FITTED.copy()
+        else:
+            start, _ = oracle.fit_data(model, x, y, err, info["params_init"])
         nres = int(NRES[name] * scale)
         res = {}
         for mapping in ("thread", "warp"):

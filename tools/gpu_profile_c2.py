@@ -1,4 +1,4 @@
-"""Short single-kernel run of the headline config (C2: n=1000, p=4) for ncu captures."""
+"""Short run of one config for ncu captures: python tools/gpu_profile_c2.py <config> <nres> <reps> <mode> <mapping>."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -9,11 +9,13 @@ name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 nres = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 mode = sys.argv[4] if len(sys.argv) > 4 else "fd"        # "fd", "analytic", "analytic+binned", "fd+binned"
+mapping = sys.argv[5] if len(sys.argv) > 5 else "thread"
 model, x, y, err = datasets.dataset(name)
 info = oracle.model_info(model)
-start, _ = oracle.fit_data(model, x, y, err, info["params_init"])
+start = datasets.C5_FITTED.copy() if name == "c5" else oracle.fit_data(model, x, y, err, info["params_init"])[0]
 ctx = fmc.Context(0)
 ctx.set_data(model, x, y, err)
+ctx.set_fit_mapping(mapping)
 if "analytic" in mode:
     ctx.set_jacobian_mode("analytic")
 if "binned" in mode:
