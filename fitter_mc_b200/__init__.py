@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     DEFAULT_SEED,
     Context,
     FmcError,
+    debug_philox4x32,
     decode_accumulator,
     derived_properties,
     finalise_moments,

@@ -76,9 +76,6 @@ struct KernelArgs {
   unsigned long long* next_id;  // work counter of this launch, zeroed beforehand
   unsigned long long* anom;     // anomaly log (fits that hit a safety cap), zeroed per launch
   double* acc;              // accumulator block, zeroed before the first chunk
-  // experimental (trial1_kernel.cuh): results of the first trial pass of call 0, computed by a
-  // uniform kernel; [flag, f, g(P), G(PP), lky(P)][cap].  nullptr = not used.
-  const double* trial1;
 };
 
 // Optional binned distributions of the fitted parameters and properties (replaces the
@@ -113,31 +110,40 @@ FMC_INLINE __device__ void kahan_add(double& s, double& c, double v) {
 }
 
 // One streaming pass of one fit over the n data points.
+// Rows beyond n (the padding to a multiple of four) are SKIPPED, not multiplied by a zero weight: a
+// model value that overflows at the padding abscissa would otherwise turn the sums into NaN
+// (inf x 0) where the reference sees an ordinary "too big" residual (toms573.f90:949-952).
 template <class M, bool INJECT, bool WITH_B, int JAC = JAC_FD>
 FMC_INLINE __device__ void pass_loop(const RowData* __restrict__ rows, const double* __restrict__ aux, int n,
                                      int n_pad, unsigned long long seed, unsigned long long id,
                                      const double* __restrict__ zrow,
                                      const PassPoint<M::NPARAM>& pa, const PassPoint<M::NPARAM>& pb,
                                      PassAcc<M::NPARAM>& acc) {
+  constexpr int NAUX = model_naux<M>::value;
+  auto row = [&](int r, float zf) {
+    const RowData rd = rows[r];
+    const double zz = INJECT ? zrow[r] : (double)zf;
+    const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
+    const double* ra = NAUX > 0 ? aux + r * NAUX : nullptr;
+    if (NAUX > 0) __builtin_assume(ra != nullptr);
+    row_accumulate<M, WITH_B, JAC>(pa, pb, rd.x, yfit, rd.rerr, acc, ra);
+  };
   // four data points per trip: one counter block of the generator yields their four deviates
-  for (int i = 0; i < n_pad; i += 4) {
+  const int n4 = n & ~3;
+  for (int i = 0; i < n4; i += 4) {
     float z[4];
     if (!INJECT) normals4(seed, id, (uint32_t)(i >> 2), z);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const RowData rd = rows[i + m];
-      double zz;
-      if (INJECT)
-        zz = (i + m < n) ? zrow[i + m] : 0.0;
-      else
-        zz = (double)z[m];
-      const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
-      constexpr int NAUX = model_naux<M>::value;
-      const double* ra = NAUX > 0 ? aux + (i + m) * NAUX : nullptr;
-      if (NAUX > 0) __builtin_assume(ra != nullptr);
-      row_accumulate<M, WITH_B, JAC>(pa, pb, rd.x, yfit, rd.rerr, acc, ra);
-    }
+    for (int m = 0; m < 4; ++m) row(i + m, z[m]);
   }
+  if (n4 < n) {  // the last, partial group
+    float z[4];
+    if (!INJECT) normals4(seed, id, (uint32_t)(n4 >> 2), z);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      if (n4 + m < n) row(n4 + m, z[m]);
+  }
+  (void)n_pad;
 }
 
 // Rows (and, NAUX > 0, the per-row auxiliary values behind them) into shared memory.
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(FMC_THREADS) init_shared_kernel(const KernelAr
 // that finishes takes the next fit from a shared counter, so lanes of a warp are at different
 // iterations of different fits but always execute the same thing next -- one trial pass
 // (residual + speculative Jacobian at x, Jacobian at x0 for the secant update).
-template <class M, bool INJECT, bool SMEM, int JAC = JAC_FD, bool TRIAL1 = false>
+template <class M, bool INJECT, bool SMEM, int JAC = JAC_FD>
 __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(const KernelArgs a) {
   constexpr int P = M::NPARAM;
   constexpr int Q = M::NPROP;
@@ -423,23 +429,6 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
       fit_passes = 1;
       active = true;
       if (s.resume()) {
-        if constexpr (TRIAL1) {
-          // The solver has just re-derived the first trial point from the initial sums, exactly as
-          // trial1_kernel did; that kernel already made the pass at it, so take its sums instead.
-          if (a.call == 0 && a.trial1[slot] != 0.0) {
-            s.res_f = a.trial1[a.cap + slot];
-#pragma unroll
-            for (int i = 0; i < P; ++i) s.res_g[i] = a.trial1[(2 + i) * a.cap + slot];
-#pragma unroll
-            for (int i = 0; i < PP; ++i) s.res_G[i] = a.trial1[(2 + P + i) * a.cap + slot];
-#pragma unroll
-            for (int i = 0; i < P; ++i) s.res_lky[i] = a.trial1[(2 + P + PP + i) * a.cap + slot];
-            fit_passes = 2;
-            if (s.resume()) return;
-            finish_call();
-            continue;
-          }
-        }
         return;
       }
       finish_call();  // ended without a single trial step (e.g. residual too big at the start)

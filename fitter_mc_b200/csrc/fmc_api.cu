@@ -15,7 +15,6 @@
 
 #include "../../include/fmc_b200.h"
 #include "model_registry.cuh"
-#include "trial1_kernel.cuh"
 #include "warp_kernel.cuh"
 
 // (no `using namespace fmc` here: fmc::exp & co. must not leak into the global scope, where
@@ -267,9 +266,6 @@ struct fmc_context {
   int comm_nranks = 1;
   int jac = fmc::JAC_FD;  // how Jacobian rows are formed (fmc_set_jacobian_mode)
   int mapping = 0;        // 0 = one fit per thread, 1 = one fit per warp (fmc_set_fit_mapping)
-  bool shared_first_trial = false;  // experimental, FMC_SHARED_FIRST_TRIAL=1 (trial1_kernel.cuh)
-  double* trial1_dev = nullptr;
-  long long trial1_cap = 0;
   double hist_lo[fmc::HIST_MAX_QUANT] = {0};
   double hist_scale[fmc::HIST_MAX_QUANT] = {0};
   long long rowj_cap = 0;
@@ -373,10 +369,6 @@ int fmc_create(fmc_context** out, int device) {
   c->acc_n = acc_len(FMC_MAX_PARAM, FMC_MAX_PARAM);
   FMC_CUDA(cudaMalloc(&c->acc_own, sizeof(double) * c->acc_n));
   c->acc = c->acc_own;
-  {
-    const char* e = std::getenv("FMC_SHARED_FIRST_TRIAL");
-    c->shared_first_trial = e && e[0] == '1';
-  }
   FMC_CUDA(cudaMalloc(&c->anom_dev, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP)));
   FMC_CUDA(cudaMemset(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP)));
   *out = owner.release();
@@ -401,7 +393,6 @@ int fmc_destroy(fmc_context* c) {
   cudaFree(c->rowj_dev);
   cudaFree(c->anom_dev);
   cudaFree(c->hist_own);
-  cudaFree(c->trial1_dev);
   cudaFree(c->params_out_dev);
   cudaFree(c->props_out_dev);
   cudaFree(c->counters_dev_out);
@@ -775,28 +766,6 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     g0_dev = c->rowj_dev + (size_t)(1 + P) * c->n_pad;
   }
 
-  // experimental: the first trial pass of call 0 as a uniform kernel that shares J(params_start)
-  const bool trial1 = c->shared_first_trial && shared_init && nresample > 0;
-  fmc::Trial1Entry t1{nullptr, nullptr, nullptr};
-  if (trial1) {
-    t1 = fmc::fmc_trial1_entry(c->model);
-    if (!t1.launch_iter) return FMC_ERR_BAD_MODEL;
-    int bps1 = 0;
-    FMC_CUDA(t1.prepare(inject, shmem_shared, shmem, &bps1));
-    if (bps1 < 1) {
-      g_last_cuda_error = "shared-first-trial kernel does not fit on an SM";
-      return FMC_ERR_CUDA;
-    }
-    const long long need = (long long)fmc::trial1_len(P) * c->chunk_cap;
-    if (need > c->trial1_cap) {
-      cudaFree(c->trial1_dev);
-      c->trial1_dev = nullptr;
-      c->trial1_cap = 0;
-      FMC_CUDA(cudaMalloc(&c->trial1_dev, sizeof(double) * need));
-      c->trial1_cap = need;
-    }
-  }
-
   if (per_warp) {
     const long long need = full_grid * (FMC_WARP_THREADS / 32) * (long long)c->n_w;
     if (need > c->tscratch_cap) {
@@ -850,13 +819,6 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
         FMC_LAUNCH(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
       else
         FMC_LAUNCH(m.launch_init(a, inject, smem, jac, shmem, c->stream));
-      if (call == 0 && trial1) {
-        FMC_LAUNCH(t1.launch_trial1(a, c->rowj_dev, c->trial1_dev, inject, shmem_shared, c->stream));
-        a.trial1 = c->trial1_dev;
-        FMC_LAUNCH(t1.launch_iter(a, inject, (int)grid, shmem, c->stream));
-        a.trial1 = nullptr;
-        continue;
-      }
       FMC_LAUNCH(m.launch_iter(a, inject, smem, jac, (int)grid, shmem, c->stream));
     }
     if (binning) {

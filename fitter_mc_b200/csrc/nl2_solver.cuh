@@ -29,11 +29,25 @@
 #pragma once
 #include "fmc_common.cuh"
 
+// The loops of the solver have compile-time trip counts (p, p(p+1)/2).  By default the compiler
+// unrolls them, which is what keeps a per-THREAD solver's small arrays in registers.  The
+// warp-per-fit kernels (warp_kernel.cuh) keep the solver state in shared memory, where dynamic
+// indexing is free, and define FMC_SOLVER_ROLLED: unrolled for p = 10 the solver is 25 000
+// instructions (400 KB) of branchy code against a 32 KB instruction cache -- measured (ncu,
+// profiles/r2_ncu_c4_warp_unrolled_summary.txt) as 4.3 "no instruction" stall cycles per issued
+// instruction, the solver step costing more than the pass over 10^4 data points it follows.
+#if defined(FMC_SOLVER_ROLLED) && defined(__CUDACC__)
+#define FMC_SOLVER_LOOP _Pragma("unroll 1")
+#else
+#define FMC_SOLVER_LOOP
+#endif
+
 namespace fmc {
 
 // ----------------------------------------------------------------- small dense helpers
 FMC_HD FMC_INLINE double dotn(int n, const double* x, const double* y) {  // dotprd, toms573.f90:2403
   double s = 0.0;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < n; ++i) s += x[i] * y[i];
   return s;
 }
@@ -44,12 +58,14 @@ FMC_HD FMC_INLINE double dotn(int n, const double* x, const double* y) {  // dot
 // scaled recurrence is kept as the fallback when the plain sum leaves the normal range.
 FMC_HD inline double nrm2_scaled(int n, const double* x) {
   int i = 0;
+  FMC_SOLVER_LOOP
   for (; i < n; ++i)
     if (x[i] != 0.0) break;
   if (i >= n) return 0.0;
   double scale = fabs(x[i]);
   if (i == n - 1) return scale;
   double t = 1.0;
+  FMC_SOLVER_LOOP
   for (int j = i + 1; j < n; ++j) {
     double xi = fabs(x[j]);
     if (!(xi > scale)) {
@@ -66,6 +82,7 @@ FMC_HD inline double nrm2_scaled(int n, const double* x) {
 }
 FMC_HD FMC_INLINE double nrm2(int n, const double* x) {
   double s = 0.0;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < n; ++i) s = fma(x[i], x[i], s);
   if (s > 1e-280 && s < 1e280) return sqrt(s);
   return nrm2_scaled(n, x);
@@ -73,14 +90,17 @@ FMC_HD FMC_INLINE double nrm2(int n, const double* x) {
 
 // Solve (L**T) x = y, L packed lower-by-rows (litvmu, toms573.f90:3334).
 FMC_HD inline void ltsolve_t(int n, double* x, const double* l, const double* y) {
+  FMC_SOLVER_LOOP
   for (int i = 0; i < n; ++i) x[i] = y[i];
   int i0 = n * (n + 1) / 2;
+  FMC_SOLVER_LOOP
   for (int i = n; i >= 1; --i) {
     double xi = x[i - 1] / l[i0 - 1];
     x[i - 1] = xi;
     if (i <= 1) return;
     i0 -= i;
     if (xi == 0.0) continue;
+    FMC_SOLVER_LOOP
     for (int j = 1; j <= i - 1; ++j) x[j - 1] -= xi * l[i0 + j - 1];
   }
 }
@@ -88,6 +108,7 @@ FMC_HD inline void ltsolve_t(int n, double* x, const double* l, const double* y)
 // Solve L x = y (livmul, toms573.f90:3367).
 FMC_HD inline void ltsolve(int n, double* x, const double* l, const double* y) {
   int kk = 1;
+  FMC_SOLVER_LOOP
   for (; kk <= n; ++kk) {
     if (y[kk - 1] != 0.0) break;
     x[kk - 1] = 0.0;
@@ -95,6 +116,7 @@ FMC_HD inline void ltsolve(int n, double* x, const double* l, const double* y) {
   if (kk > n) return;
   int j = kk * (kk + 1) / 2;
   x[kk - 1] = y[kk - 1] / l[j - 1];
+  FMC_SOLVER_LOOP
   for (int i = kk + 1; i <= n; ++i) {
     double t = dotn(i - 1, &l[j], x);
     j += i;
@@ -106,11 +128,14 @@ FMC_HD inline void ltsolve(int n, double* x, const double* l, const double* y) {
 // the first non-positive reduced diagonal (stored in place of the diagonal).
 FMC_HD inline int chol_rows(int n, double* l, const double* a) {
   int i0 = 0;
+  FMC_SOLVER_LOOP
   for (int i = 1; i <= n; ++i) {
     double td = 0.0;
     int j0 = 0;
+    FMC_SOLVER_LOOP
     for (int j = 1; j <= i - 1; ++j) {
       double t = 0.0;
+      FMC_SOLVER_LOOP
       for (int m = 1; m <= j - 1; ++m) t += l[i0 + m - 1] * l[j0 + m - 1];
       j0 += j;
       t = (a[i0 + j - 1] - t) / l[j0 - 1];
@@ -131,14 +156,17 @@ FMC_HD inline int chol_rows(int n, double* l, const double* a) {
 // y = S x for packed lower-by-rows symmetric S (slvmul, toms573.f90:4697).
 FMC_HD inline void symv(int p, double* y, const double* s, const double* x) {
   int j = 0;
+  FMC_SOLVER_LOOP
   for (int i = 1; i <= p; ++i) {
     y[i - 1] = dotn(i, &s[j], x);
     j += i;
   }
   j = 0;
+  FMC_SOLVER_LOOP
   for (int i = 2; i <= p; ++i) {
     double xi = x[i - 1];
     j += 1;
+    FMC_SOLVER_LOOP
     for (int m = 1; m <= i - 1; ++m) {
       y[m - 1] += s[j] * xi;
       j += 1;
@@ -199,12 +227,14 @@ struct Nl2 {
 
   // nl2sno fresh start (toms573.f90:688-700): D = 1 for the first finite-difference Jacobian.
   FMC_HD void begin(const double* xs) {
+    FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i) {
       x[i] = xs[i];
       x0[i] = xs[i];
       d[i] = 1.0;
     }
     set_fd_steps();
+    FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i) hJ[i] = hA[i];
     need_b = 0;
     phase = PH_INIT;
@@ -213,6 +243,7 @@ struct Nl2 {
 
   // Finite-difference steps for the next Jacobian (toms573.f90:716).
   FMC_HD void set_fd_steps() {
+    FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i) hA[i] = k::dltfdj * fmax(fabs(x[i]), 1.0 / d[i]);
   }
 
@@ -245,11 +276,13 @@ FMC_HD void Nl2<P>::init_iteration_state() {
   kalm = -1;
   radinc = 0;
   hvalid = 0;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) d[i] = 0.0;  // v(dinit) = 0: D is then set entirely by dupdat
   v[RAD0] = 0.0;
   v[STPPAR] = 0.0;
   v[RADIUS] = k::lmax0 / (1.0 + k::phmxfc);
   model = 1;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < PP; ++i) S[i] = 0.0;
 }
 
@@ -257,13 +290,16 @@ FMC_HD void Nl2<P>::init_iteration_state() {
 template <int P>
 FMC_HD void Nl2<P>::adopt_jacobian() {
   kalm = -1;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) {
     g[i] = res_g[i];
     hJ[i] = hA[i];
   }
+  FMC_SOLVER_LOOP
   for (int i = 0; i < PP; ++i) G[i] = res_G[i];
   // dupdat (toms573.f90:2434-2468) with ||J(:,i)|| = sqrt(G_ii)
   int s1 = -1;
+  FMC_SOLVER_LOOP
   for (int i = 1; i <= P; ++i) {
     s1 += i;
     double sii = S[s1];
@@ -272,6 +308,7 @@ FMC_HD void Nl2<P>::adopt_jacobian() {
     if (t < k::jtinit) t = fmax(k::d0init, k::jtinit);
     d[i - 1] = fmax(k::dfac * d[i - 1], t);
   }
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) dig[i] = g[i] / d[i];
   v[DGNORM] = nrm2(P, dig);
 }
@@ -284,21 +321,27 @@ FMC_HD void Nl2<P>::factor() {
   double A[P][P];
   {
     int m = 0;
+    FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i)
+      FMC_SOLVER_LOOP
       for (int j = 0; j <= i; ++j) {
         A[i][j] = G[m];
         A[j][i] = G[m];
         ++m;
       }
   }
+  FMC_SOLVER_LOOP
   for (int j = 0; j < P; ++j) ipivot[j] = j + 1;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < PP; ++i) rfac[i] = 0.0;
   ierr = 0;
   int rank = P;
 #define FMC_R(i, j) rfac[(j) * ((j) + 1) / 2 + (i)]  // 0-based (i <= j)
+  FMC_SOLVER_LOOP
   for (int kk = 0; kk < P; ++kk) {
     double sigma = 0.0;
     int jbar = -1;
+    FMC_SOLVER_LOOP
     for (int j = kk; j < P; ++j) {
       if (sigma >= A[j][j]) continue;
       sigma = A[j][j];
@@ -313,16 +356,19 @@ FMC_HD void Nl2<P>::factor() {
       int ti = ipivot[kk];
       ipivot[kk] = ipivot[jbar];
       ipivot[jbar] = ti;
+      FMC_SOLVER_LOOP
       for (int i = 0; i < P; ++i) {
         double t = A[i][kk];
         A[i][kk] = A[i][jbar];
         A[i][jbar] = t;
       }
+      FMC_SOLVER_LOOP
       for (int i = 0; i < P; ++i) {
         double t = A[kk][i];
         A[kk][i] = A[jbar][i];
         A[jbar][i] = t;
       }
+      FMC_SOLVER_LOOP
       for (int i = 0; i < kk; ++i) {
         double t = FMC_R(i, kk);
         FMC_R(i, kk) = FMC_R(i, jbar);
@@ -331,8 +377,11 @@ FMC_HD void Nl2<P>::factor() {
     }
     double rkk = sqrt(A[kk][kk]);
     FMC_R(kk, kk) = rkk;
+    FMC_SOLVER_LOOP
     for (int j = kk + 1; j < P; ++j) FMC_R(kk, j) = A[kk][j] / rkk;
+    FMC_SOLVER_LOOP
     for (int i = kk + 1; i < P; ++i)
+      FMC_SOLVER_LOOP
       for (int j = i; j < P; ++j) {
         double t = A[i][j] - FMC_R(kk, i) * FMC_R(kk, j);
         A[i][j] = t;
@@ -340,12 +389,14 @@ FMC_HD void Nl2<P>::factor() {
       }
   }
   // qtr = R^-T P^T g on the leading `rank` rows
+  FMC_SOLVER_LOOP
   for (int kk = 0; kk < P; ++kk) {
     if (kk >= rank) {
       qtr[kk] = 0.0;
       continue;
     }
     double t = g[ipivot[kk] - 1];
+    FMC_SOLVER_LOOP
     for (int i = 0; i < kk; ++i) t -= FMC_R(i, kk) * qtr[i];
     qtr[kk] = t / FMC_R(kk, kk);
   }
@@ -357,8 +408,10 @@ FMC_HD void Nl2<P>::factor() {
 template <int P>
 FMC_HD void Nl2<P>::build_h() {
   int m = 0;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) {
     double t = 1.0 / d[i];
+    FMC_SOLVER_LOOP
     for (int j = 0; j <= i; ++j) {
       hmat[m] = t * (G[m] + S[m]) / d[j];
       ++m;
@@ -370,28 +423,36 @@ FMC_HD void Nl2<P>::build_h() {
 template <int P>
 FMC_HD void Nl2<P>::hess_times_step() {
   if (stpmod == 2) {
+    FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i) tmp2[i] = d[i] * step[i];
     symv(P, tmp1, hmat, tmp2);
+    FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i) tmp1[i] = d[i] * tmp1[i];
     return;
   }
   // rptmul(2,...): perm * R^T * R * perm^T * step (toms573.f90:4595-4655)
   double z[P], y[P];
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) z[i] = step[ipivot[i] - 1];
 #define FMC_R(i, j) rfac[(j) * ((j) + 1) / 2 + (i)]
   y[0] = z[0] * FMC_R(0, 0);
+  FMC_SOLVER_LOOP
   for (int kk = 1; kk < P; ++kk) {
     double zk = z[kk];
+    FMC_SOLVER_LOOP
     for (int i = 0; i < kk; ++i) y[i] += FMC_R(i, kk) * zk;
     y[kk] = zk * FMC_R(kk, kk);
   }
   z[0] = y[0] * FMC_R(0, 0);
+  FMC_SOLVER_LOOP
   for (int i = 1; i < P; ++i) {
     double t = 0.0;
+    FMC_SOLVER_LOOP
     for (int m = 0; m < i; ++m) t += FMC_R(m, i) * y[m];
     z[i] = y[i] * FMC_R(i, i) + t;
   }
 #undef FMC_R
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) tmp1[ipivot[i] - 1] = z[i];
 }
 
@@ -406,13 +467,17 @@ FMC_HD void Nl2<P>::slupdt(const double* wchmtd) {
   if (denmin != 0.0) wscale_ = fmin(1.0, fabs(sdotwm / denmin));
   double t = 0.0;
   if (sdotwm != 0.0) t = wscale_ / sdotwm;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) ww[i] = t * wchmtd[i];
   symv(P, u, S, step);
   t = 0.5 * (size_ * dotn(P, step, u) - dotn(P, step, lky));
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) u[i] = t * ww[i] + lky[i] - size_ * u[i];
   int m = 0;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) {
     double ui = u[i], wi = ww[i];
+    FMC_SOLVER_LOOP
     for (int j = 0; j <= i; ++j) {
       S[m] = size_ * S[m] + ui * ww[j] + wi * u[j];
       ++m;
@@ -495,6 +560,7 @@ L80:
 L90: {
   // reldst (toms573.f90:4570-4592)
   double em = 0.0, xm = 0.0;
+  FMC_SOLVER_LOOP
   for (int m = 0; m < P; ++m) {
     double t = fabs(d[m] * (x[m] - x0[m]));
     if (em < t) em = t;
@@ -505,6 +571,7 @@ L90: {
   if (xm > 0.0) reldx1 = em / xm;
 }
   if (goodx) goto L110;
+  FMC_SOLVER_LOOP
   for (int m = 0; m < P; ++m) {
     step[m] = stlstg[m];
     x[m] = x0[m] + stlstg[m];
@@ -518,6 +585,7 @@ L110:
   mlstgd = model;
   v[FLSTGD] = v[F];
   v[F] = v[F0];
+  FMC_SOLVER_LOOP
   for (int m = 0; m < P; ++m) x[m] = x0[m];
   x_is_eval = 0;
   restor = 1;
@@ -568,6 +636,7 @@ L190:
 L200:
   v[FLSTGD] = v[F];
   mlstgd = model;
+  FMC_SOLVER_LOOP
   for (int m = 0; m < P; ++m) stlstg[m] = step[m];
   v[DSTSAV] = v[DSTNRM];
   nfgcal = nfc;
@@ -613,11 +682,13 @@ L270:
   if (irc == 12) v[DSTSAV] = -v[DSTSAV];
   v[PLSTGD] = v[PREDUC];
   irc = 6;
+  FMC_SOLVER_LOOP
   for (int m = 0; m < P; ++m) stlstg[m] = step[m];
   return;
 L280:
   v[GTSTEP] = v[GTSLST];
   v[DSTNRM] = fabs(v[DSTSAV]);
+  FMC_SOLVER_LOOP
   for (int m = 0; m < P; ++m) step[m] = stlstg[m];
   irc = xirc;
   if (v[DSTSAV] <= 0.0) irc = 12;
@@ -683,6 +754,7 @@ L20:
   v[DST0] = -1.0;
   if (ierr != 0) goto L50;
   ltsolve_t(p, w, hmat, qtr);
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     st[i] = dd[j1] * ww[i];
@@ -692,6 +764,7 @@ L20:
   phi = dst - rad;
   if (phi <= phimax) goto L350;
   if (ka > 0) goto L70;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     st[i] = dd[j1] * (st[i] / dst);
@@ -701,6 +774,7 @@ L20:
   ww[phipin] = (t / dst) * t;
   lk = phi * ww[phipin];
 L50:
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) ww[i] = gg[i] / dd[i];
   v[DGNORM] = nrm2(p, w);
   uk = v[DGNORM] / rad;
@@ -712,12 +786,16 @@ L70:
     goto L370;
   }
   ka = ka + 1;
+  FMC_SOLVER_LOOP
   for (i = 0; i < pp1o2; ++i) ww[rmat + i] = hmat[i];
+  FMC_SOLVER_LOOP
   for (i = 0; i < p; ++i) ww[res + i] = qtr[i];
   if (alphak <= 0.0 || alphak < lk || alphak >= uk) alphak = uk * fmax(p001, sqrt(lk / uk));
   sqrtak = sqrt(alphak);
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) ww[i] = 1.0;
 
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     l = i * (i + 1) / 2 + rmat0;
     wl = ww[l];
@@ -735,6 +813,7 @@ L70:
     d2 = d2 / t;
     ww[l] = t * wl;
     a = -a;
+    FMC_SOLVER_LOOP
     for (j1 = i; j1 <= p; ++j1) {
       l = l + j1;
       st[j1] = a * ww[l];
@@ -748,6 +827,7 @@ L70:
     ww[i] = d2 / t;
     d2 = d1 / t;
     ww[l] = t * adi;
+    FMC_SOLVER_LOOP
     for (j1 = i; j1 <= p; ++j1) {
       l = l + j1;
       wl = ww[l];
@@ -757,6 +837,7 @@ L70:
   L130:
     if (i == p) goto L240;
     ip1 = i + 1;
+    FMC_SOLVER_LOOP
     for (i1 = ip1; i1 <= p; ++i1) {
       l = i1 * (i1 + 1) / 2 + rmat0;
       wl = ww[l];
@@ -766,6 +847,7 @@ L70:
       d1 = d1 * dfacsq;
       wl = wl / dfac;
       kk = l;
+      FMC_SOLVER_LOOP
       for (j1 = i1; j1 <= p; ++j1) {
         kk = kk + j1;
         ww[kk] = ww[kk] / dfac;
@@ -781,6 +863,7 @@ L70:
       ww[l] = t * wl;
       ww[i1] = d1 / t;
       d2 = d2 / t;
+      FMC_SOLVER_LOOP
       for (j1 = i1; j1 <= p; ++j1) {
         l = l + j1;
         wl = ww[l];
@@ -797,6 +880,7 @@ L70:
       ww[i1] = d2 / t;
       d2 = d1 / t;
       ww[l] = t * si;
+      FMC_SOLVER_LOOP
       for (j1 = i1; j1 <= p; ++j1) {
         l = l + j1;
         wl = ww[l];
@@ -807,11 +891,13 @@ L70:
     L200:
       if (d2 >= dtol) continue;
       d2 = d2 * dfacsq;
+      FMC_SOLVER_LOOP
       for (kk = i1; kk <= p; ++kk) st[kk] = st[kk] / dfac;
     }
   }
 L240:
   ltsolve_t(p, &ww[res], &ww[rmat], &ww[res]);
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     kk = res0 + i;
@@ -836,12 +922,14 @@ L260:
 L270:
   if (phi < 0.0) uk = alphak;
 L280:
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     kk = res0 + i;
     st[i] = dd[j1] * (ww[kk] / dst);
   }
   ltsolve(p, step, &ww[rmat], step);
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) st[i] = st[i] / sqrt(ww[i]);
   t = 1.0 / nrm2(p, step);
   alphak = alphak + t * phi * t / rad;
@@ -872,10 +960,12 @@ L330:
   uk = 0.0;
   v[GTSTEP] = 0.0;
   v[PREDUC] = 0.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) st[i] = 0.0;
   goto L390;
 L350:
   alphak = 0.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     st[j1] = -ww[i];
@@ -901,12 +991,14 @@ FMC_HD double Nl2<P>::lsvmin(const double* l_, double* x_, double* y_) {
   double* yv = y_ - 1;
   const int p = P;
   int ii = 0;
+  FMC_SOLVER_LOOP
   for (int i = 1; i <= p; ++i) {
     xv[i] = 0.0;
     ii += i;
     if (l[ii] == 0.0) return 0.0;
   }
   if (lsvmin_ix % 9973 == 0) lsvmin_ix = 2;
+  FMC_SOLVER_LOOP
   for (int j = p; j >= 1; --j) {
     lsvmin_ix = (3432 * lsvmin_ix) % 9973;
     double b = 0.5 * (1.0 + (double)lsvmin_ix / 9973.0);
@@ -919,19 +1011,24 @@ FMC_HD double Nl2<P>::lsvmin(const double* l_, double* x_, double* y_) {
     int jj = j0 + j;
     xplus = xplus / l[jj];
     xminus = xminus / l[jj];
+    FMC_SOLVER_LOOP
     for (int i = 1; i <= jm1; ++i) {
       splus += fabs(xv[i] + l[j0 + i] * xplus);
       sminus += fabs(xv[i] + l[j0 + i] * xminus);
     }
     if (sminus > splus) xplus = xminus;
     xv[j] = xplus;
+    FMC_SOLVER_LOOP
     for (int i = 1; i <= jm1; ++i) xv[i] += l[j0 + i] * xplus;
   }
   double t = 1.0 / nrm2(p, x_);
+  FMC_SOLVER_LOOP
   for (int i = 1; i <= p; ++i) xv[i] = t * xv[i];
+  FMC_SOLVER_LOOP
   for (int j = 1; j <= p; ++j) {
     double psj = 0.0;
     int j0 = j * (j - 1) / 2;
+    FMC_SOLVER_LOOP
     for (int i = 1; i <= j - 1; ++i) psj += l[j0 + i] * yv[i];
     yv[j] = (xv[j] - psj) / l[j0 + j];
   }
@@ -996,11 +1093,13 @@ FMC_HD void Nl2<P>::gqtstp() {
   ka = 0;
   kalim = 50;
   j = 0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j += i;
     ww[diag0 + i] = dihdi[j];
   }
   t1 = 0.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= PP; ++i) {
     t = fabs(dihdi[i]);
     if (t1 < t) t1 = t;
@@ -1012,6 +1111,7 @@ L30:
   j = irc_ * (irc_ + 1) / 2;
   t = l[j];
   l[j] = 1.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= irc_; ++i) ww[i] = 0.0;
   ww[irc_] = 1.0;
   ltsolve_t(irc_, w, lmat, w);
@@ -1036,10 +1136,12 @@ L60:
   v[DGNORM] = nrm2(p, dig);
   if (v[DGNORM] == 0.0) goto L430;
   kk = 0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     wi = 0.0;
     if (i != 1) {
       im1 = i - 1;
+      FMC_SOLVER_LOOP
       for (j = 1; j <= im1; ++j) {
         kk = kk + 1;
         t = fabs(dihdi[kk]);
@@ -1052,6 +1154,7 @@ L60:
   }
   kk = 1;
   t1 = ww[diag] - ww[1];
+  FMC_SOLVER_LOOP
   for (i = 2; i <= p; ++i) {
     j = diag0 + i;
     t = ww[j] - ww[i];
@@ -1065,6 +1168,7 @@ L60:
   k1 = kk * (kk - 1) / 2 + 1;
   inc = 1;
   t = 0.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     if (i == kk) goto L120;
     aki = fabs(dihdi[k1]);
@@ -1083,6 +1187,7 @@ L60:
   uk = v[DGNORM] / rad - ww[emin];
   kk = 1;
   t1 = ww[diag] + ww[1];
+  FMC_SOLVER_LOOP
   for (i = 2; i <= p; ++i) {
     j = diag0 + i;
     t = ww[j] + ww[i];
@@ -1096,6 +1201,7 @@ L60:
   k1 = kk * (kk - 1) / 2 + 1;
   inc = 1;
   t = 0.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     if (i == kk) goto L170;
     aki = fabs(dihdi[k1]);
@@ -1127,6 +1233,7 @@ L200:
   ka = ka + 1;
   if (-v[DST0] >= alphak || alphak < lk || alphak >= uk) alphak = uk * fmax(p001, sqrt(lk / uk));
   kk = 0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     kk = kk + i;
     dihdi[kk] = ww[diag0 + i] + alphak;
@@ -1136,6 +1243,7 @@ L200:
   j = (irc_ * (irc_ + 1)) / 2;
   t = l[j];
   l[j] = 1.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= irc_; ++i) ww[i] = 0.0;
   ww[irc_] = 1.0;
   ltsolve_t(irc_, w, lmat, w);
@@ -1171,6 +1279,7 @@ L250:
 L260:
   alphak = 0.0;
 L270:
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) st[i] = -ww[q0 + i] / dd[i];
   v[GTSTEP] = -dotn(p, dig, &ww[q]);
   v[PREDUC] = 0.5 * (fabs(alphak) * dst * dst - v[GTSTEP]);
@@ -1180,6 +1289,7 @@ L290:
   restrt = true;
   ka = ka + 1;
   kk = 0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     kk = kk + i;
     dihdi[kk] = ww[diag0 + i];
@@ -1213,6 +1323,7 @@ L330:
   t = lsvmin(lmat, &ww[xx], w);
   kk = 0;
 L340:
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) ww[i] = t * ww[i];
   ltsolve_t(p, w, lmat, w);
   t1 = 1.0 / nrm2(p, w);
@@ -1220,11 +1331,13 @@ L340:
   if (t <= delta) goto L370;
   if (kk > 30) goto L270;
   kk = kk + 1;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) ww[x00 + i] = t1 * ww[i];
   ltsolve(p, w, lmat, &ww[xx]);
   t = 1.0 / nrm2(p, w);
   goto L340;
 L370:
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) ww[i] = t1 * ww[i];
   sw = dotn(p, &ww[q], w);
   t1 = (rad + dst) * (rad - dst);
@@ -1239,6 +1352,7 @@ L370:
   dst = rad;
   t1 = -si;
 L390:
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j = q0 + i;
     ww[j] = t1 * ww[i] - ww[j];
@@ -1253,6 +1367,7 @@ L410:
   v[RAD0] = rad;
   ww[dstsav] = dst;
   j = 0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) {
     j += i;
     dihdi[j] = ww[diag0 + i];
@@ -1263,6 +1378,7 @@ L430:
   v[PREDUC] = 0.0;
   v[DSTNRM] = 0.0;
   v[GTSTEP] = 0.0;
+  FMC_SOLVER_LOOP
   for (i = 1; i <= p; ++i) st[i] = 0.0;
 }
 
@@ -1299,6 +1415,7 @@ L100:
     int kk = niter;
     niter = kk + 1;
     if (kk != 0) {
+      FMC_SOLVER_LOOP
       for (int i = 0; i < P; ++i) step[i] = d[i] * step[i];
       v[RADIUS] = v[RADFAC] * nrm2(P, step);
     }
@@ -1309,6 +1426,7 @@ L100:
   irc = 4;
   hvalid = 0;
   sused = model;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) x0[i] = x[i];
 
 L160:
@@ -1329,6 +1447,7 @@ L180:
   if (model == 2) goto L220;
   if (kalm < 0) factor();
   if (!hvalid) {
+    FMC_SOLVER_LOOP
     for (int i = 0; i < PP; ++i) hmat[i] = rfac[i];
     hvalid = 1;
   }
@@ -1343,6 +1462,7 @@ L220:
 
 L290:
   if (irc == 6) goto L300;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) x[i] = step[i] + x0[i];
   nfcall = nfcall + 1;
   toobig = 0;
@@ -1357,6 +1477,7 @@ L300:
   if (trace && trace_len < trace_cap) {
     double* t = trace + (size_t)trace_len * 10;
     double piv = 0.0;
+    FMC_SOLVER_LOOP
     for (int q = 0; q < P; ++q) piv = piv * P + (ipivot[q] - 1);
     t[0] = irc;
     t[1] = sused;
@@ -1374,6 +1495,7 @@ L300:
   if (swtch != 0) {
     hvalid = 0;
     sused = sused + 2;
+    FMC_SOLVER_LOOP
     for (int i = 0; i < 9; ++i) v[i] = vsave[i];
   }
   l = irc - 4;
@@ -1397,6 +1519,7 @@ L300:
   if (-2 < l) goto L380;
   hvalid = 0;
   sused = sused + 2;
+  FMC_SOLVER_LOOP
   for (int i = 0; i < 9; ++i) vsave[i] = v[i];
   goto L160;  // label 350 only saves r, which is not kept here
 L330:
@@ -1426,14 +1549,18 @@ L380:
     return true;
   }
 L385:
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) lky[i] = res_lky[i];  // lky = J(x0)^T r(x), toms573.f90:1268-1293
   if (irc == 3) hess_times_step();                  // label 410
   ngcall = ngcall + 1;                              // label 450
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) w[i] = g[i];          // g0
   adopt_jacobian();                                 // labels 50-60 at the new x
   // label 460
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) w[i] = -w[i] + g[i];  // g - g0
   if (irc == 3) {
+    FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i) tmp1[i] = (tmp1[i] - w[i]) / d[i];
     if (nrm2(P, tmp1) <= v[DGNORM] * k::tuner4) {
       v[RADFAC] = k::incfac;
@@ -1443,6 +1570,7 @@ L385:
     }
   }
   // label 490: y = (J(x) - J(x0))^T r(x), sizing factor, secant update of S
+  FMC_SOLVER_LOOP
   for (int i = 0; i < P; ++i) lky[i] = -lky[i] + g[i];
   symv(P, tmp1, S, step);
   t1 = fabs(dotn(P, step, tmp1));

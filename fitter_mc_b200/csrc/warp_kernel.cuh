@@ -103,13 +103,12 @@ FMC_INLINE __device__ void sweep_a(const WarpCols& c, int n, int n_w, int lane, 
     if (!INJECT) normals4(seed, id, (uint32_t)blk, z);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
+      // rows beyond n (padding) are skipped, not given a zero weight: a model value that overflows
+      // there would turn the sums into NaN (inf x 0) instead of an ordinary "too big" residual
+      if (4 * blk + m >= n) continue;
       const int s = (4 * j + m) * 32 + lane;
       const double xi = c.x[s], yi = c.y[s], ei = c.err[s], wi = c.rerr[s];
-      double zz;
-      if (INJECT)
-        zz = (4 * blk + m < n) ? zrow[4 * blk + m] : 0.0;
-      else
-        zz = (double)z[m];
+      const double zz = INJECT ? zrow[4 * blk + m] : (double)z[m];
       const double yfit = fma(zz, ei, yi);  // offset_data, bootstrap.f90:208
       double m0, dma[P];
       double ra[NAUX > 0 ? NAUX : 1];
@@ -137,13 +136,14 @@ FMC_INLINE __device__ void sweep_a(const WarpCols& c, int n, int n_w, int lane, 
 
 // Sweep B: lky = J(pb)^T r(pa), from the t_i that sweep A left in tbuf.
 template <class M, int JAC>
-FMC_INLINE __device__ void sweep_b(const WarpCols& c, int n_w, int lane, const PassPoint<M::NPARAM>& pb,
+FMC_INLINE __device__ void sweep_b(const WarpCols& c, int n, int n_w, int lane, const PassPoint<M::NPARAM>& pb,
                                    const double* __restrict__ tbuf, double (&lky)[M::NPARAM]) {
   constexpr int P = M::NPARAM;
 #pragma unroll
   for (int i = 0; i < P; ++i) lky[i] = 0.0;
 #pragma unroll 4
   for (int s = lane; s < n_w; s += 32) {
+    if (4 * (32 * (s >> 7) + lane) + ((s >> 5) & 3) >= n) continue;  // padding row (see sweep_a)
     const double xi = c.x[s];
     const double t = tbuf[s];
     double mb, dmb[P];
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
       PassPoint<P> pb;
       pb.set(s.x0, hb);
       double lky[P];
-      sweep_b<M, JAC>(c, n_w, lane, pb, tbuf, lky);
+      sweep_b<M, JAC>(c, a.n, n_w, lane, pb, tbuf, lky);
       if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < P; ++i) s.res_lky[i] = JAC == JAC_ANALYTIC ? lky[i] : lky[i] * (1.0 / hb[i]);
@@ -318,12 +318,13 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
         }
       }
       __syncwarp();
-      int passes = 1;
-      // first evaluation of the call: residual + Jacobian at the starting point, D = 1
-      pass(std::false_type{}, id, zrow);
-      bool more = step(passes);
-      while (more) {
-        pass(std::true_type{}, id, zrow);
+      int passes = 0;
+      bool more = true;
+      while (more) {  // (one call site of the solver step: its code exists once)
+        if (passes == 0)
+          pass(std::false_type{}, id, zrow);  // first evaluation of the call: residual + Jacobian at the start, D = 1
+        else
+          pass(std::true_type{}, id, zrow);
         ++passes;
         more = step(passes);
       }
@@ -389,12 +390,14 @@ __global__ void __launch_bounds__(FMC_WARP_THREADS, 1) warp_fit_kernel(const Ker
       for (int w = 0; w < FMC_WARP_THREADS / 32; ++w) t += red[w];
     return t;
   };
+#pragma unroll 1
   for (int i = 0; i < NM; ++i) {
     const double t = block_sum(msum[i] - mcmp[i]);
     if (threadIdx.x == 0) atomicAdd(&a.acc[i], t);
   }
   const double tails[5] = {(double)n_fit, (double)n_fcall, (double)n_gcall, (double)n_iter, (double)n_pass};
   const int tail_idx[5] = {ACC_NFIT, ACC_NFCALL, ACC_NGCALL, ACC_NITER, ACC_NPASS};
+#pragma unroll 1
   for (int i = 0; i < 5; ++i) {
     const double t = block_sum(tails[i]);
     if (threadIdx.x == 0) atomicAdd(&a.acc[NM + tail_idx[i]], t);

@@ -269,111 +269,6 @@ int bootstrap_warp(int n, const double* x, const double* y, const double* err, c
   return disagreements;
 }
 
-// ---- host image of the experimental shared-first-trial path (csrc/trial1_kernel.cuh): the first
-// trial pass of the first solver call takes J(params_start)^T r(x) from Jacobian rows evaluated
-// once at params_start (what jac0_kernel stores) instead of re-evaluating the model there.
-double g_trial1_lky_diff = 0.0;  // worst relative difference between lky from the shared rows and from a
-                                 // re-evaluation at x0 (what the normal flow does), over all emulated fits
-
-template <class M>
-int fit_one_trial1(int n, const double* x, const double* yfit, const double* err, const double* rowJ,
-                   double* params, int* counters) {
-  constexpr int P = M::NPARAM;
-  std::vector<double> rerr(n);
-  for (int i = 0; i < n; ++i) rerr[i] = 1.0 / err[i];
-  Nl2<P> s;
-  std::memset(&s, 0, sizeof(s));
-  s.reset_fit();
-  for (int call = 0; call < 2; ++call) {
-    s.begin(params);
-    int npass = 0;
-    bool first_trial = call == 0;
-    for (;;) {
-      if (npass == 1 && first_trial) {
-        // the trial1_kernel pass: A part as usual, lky from the shared rows
-        PassPoint<P> a;
-        a.set(s.x, s.hA);
-        PassAcc<P> acc;
-        acc.zero();
-        for (int i = 0; i < n; ++i) {
-          double m0, dma[P];
-          row_model<M>(a, x[i], m0, dma);
-          const double r = (yfit[i] - m0) * rerr[i];
-          const double t = rerr[i] * r, w2 = rerr[i] * rerr[i];
-          acc.f = fma(r, r, acc.f);
-          int q = 0;
-          for (int ii = 0; ii < P; ++ii) {
-            acc.g[ii] = fma(dma[ii], t, acc.g[ii]);
-            const double dw = dma[ii] * w2;
-            for (int jj = 0; jj <= ii; ++jj) {
-              acc.G[q] = fma(dw, dma[jj], acc.G[q]);
-              ++q;
-            }
-          }
-          for (int kk = 0; kk < P; ++kk) acc.lky[kk] = fma(rowJ[i * (1 + P) + 1 + kk], r, acc.lky[kk]);
-        }
-        {  // cross-check against the normal flow's J(x0)^T r(x) (model re-evaluated at x0 with steps hJ)
-          PassPoint<P> b;
-          b.set(s.x0, s.hJ);
-          PassAcc<P> ref;
-          ref.zero();
-          for (int i = 0; i < n; ++i) row_accumulate<M, true>(a, b, x[i], yfit[i], rerr[i], ref);
-          double num = 0.0, den = 0.0;
-          for (int kk = 0; kk < P; ++kk) {
-            num = std::fmax(num, std::fabs(acc.lky[kk] - ref.lky[kk]));
-            den = std::fmax(den, std::fabs(ref.lky[kk]));
-          }
-          if (den > 0.0) g_trial1_lky_diff = std::fmax(g_trial1_lky_diff, num / den);
-        }
-        pass_finish<P>(acc, s);
-      } else {
-        run_pass<M>(s, n, x, yfit, rerr.data());
-      }
-      ++npass;
-      if (!s.resume()) break;
-      if (npass > 2 * (k::mxfcal + k::mxiter)) break;
-    }
-    for (int i = 0; i < P; ++i) params[i] = s.x[i];
-    if (counters) {
-      int* c = counters + 5 * call;
-      c[0] = s.rc;
-      c[1] = s.nfcall;
-      c[2] = s.ngcall;
-      c[3] = s.niter;
-      c[4] = npass;
-    }
-  }
-  return 0;
-}
-
-template <class M>
-int bootstrap_trial1(int n, const double* x, const double* y, const double* err, const double* start, long long nres,
-                     const double* z, double* params_out, int* counters_out) {
-  constexpr int P = M::NPARAM;
-  // jac0_kernel: rowJ[i][0] = m0_i, rowJ[i][1+k] = dm_ik / err_i at params_start, steps with D = 1
-  std::vector<double> rowJ((size_t)n * (1 + P));
-  {
-    double h[P];
-    for (int i = 0; i < P; ++i) h[i] = k::dltfdj * std::fmax(std::fabs(start[i]), 1.0);
-    PassPoint<P> pt;
-    pt.set(start, h);
-    for (int i = 0; i < n; ++i) {
-      double m0, dm[P];
-      row_model<M>(pt, x[i], m0, dm);
-      rowJ[(size_t)i * (1 + P)] = m0;
-      for (int kk = 0; kk < P; ++kk) rowJ[(size_t)i * (1 + P) + 1 + kk] = dm[kk] * (1.0 / err[i]);
-    }
-  }
-  std::vector<double> yfit(n), p(P);
-  for (long long r = 0; r < nres; ++r) {
-    for (int i = 0; i < n; ++i) yfit[i] = fma(z[(size_t)r * n + i], err[i], y[i]);
-    for (int i = 0; i < P; ++i) p[i] = start[i];
-    fit_one_trial1<M>(n, x, yfit.data(), err, rowJ.data(), p.data(), counters_out ? counters_out + 10 * r : nullptr);
-    std::memcpy(params_out + (size_t)r * P, p.data(), sizeof(double) * P);
-  }
-  return 0;
-}
-
 // model value and forward differences dm[k] = m(x) - m(x + h_k e_k) through (a) the product's
 // row_model (perturbation arithmetic for generic plug-ins) and (b) p+1 plain evaluations
 template <class M>
@@ -523,24 +418,6 @@ int emul_bootstrap_warp(int model, int jac, int n, const double* x, const double
     WARP_CASE(3, ModelStiff4)
   }
 #undef WARP_CASE
-  return -1;
-}
-
-double emul_trial1_lky_diff(int reset) {
-  const double v = g_trial1_lky_diff;
-  if (reset) g_trial1_lky_diff = 0.0;
-  return v;
-}
-
-int emul_bootstrap_trial1(int model, int n, const double* x, const double* y, const double* err,
-                          const double* start, long long nres, const double* z, double* params_out,
-                          int* counters_out) {
-  switch (model) {
-    case 0: return bootstrap_trial1<ModelUser>(n, x, y, err, start, nres, z, params_out, counters_out);
-    case 1: return bootstrap_trial1<ModelTest4>(n, x, y, err, start, nres, z, params_out, counters_out);
-    case 2: return bootstrap_trial1<ModelPeaks10>(n, x, y, err, start, nres, z, params_out, counters_out);
-    case 3: return bootstrap_trial1<ModelStiff4>(n, x, y, err, start, nres, z, params_out, counters_out);
-  }
   return -1;
 }
 

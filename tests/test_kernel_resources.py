@@ -40,11 +40,11 @@ def test_sm_100a_only(usage):
 
 @pytest.mark.parametrize("model,solver_stack", [("9ModelUser", 1232), ("10ModelTest4", 1648), ("11ModelStiff4", 1648)])
 def test_refill_kernels_of_small_models_do_not_spill(usage, model, solver_stack):
-    # iterate_kernel<M, INJECT=0, SMEM=1, JAC_FD, TRIAL1=0>: the kernel bench.py times
-    regs, stack = _find(usage, "iterate_kernelINS_" + model + "ELb0ELb1ELi0ELb0E")
+    # iterate_kernel<M, INJECT=0, SMEM=1, JAC_FD>: the kernel bench.py times
+    regs, stack = _find(usage, "iterate_kernelINS_" + model + "ELb0ELb1ELi0EEEv")
     assert regs * 256 <= 65536
     assert stack == solver_stack                                     # the solver's arrays, no spill slots
-    regs_a, stack_a = _find(usage, "iterate_kernelINS_" + model + "ELb0ELb1ELi1ELb0E")   # analytic mode
+    regs_a, stack_a = _find(usage, "iterate_kernelINS_" + model + "ELb0ELb1ELi1EEEv")   # analytic mode
     assert regs_a * 256 <= 65536 and stack_a == solver_stack
 
 

@@ -28,7 +28,7 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
-SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12,
+SCALE = {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12,
          "msecond": 1e-3, "usecond": 1e-6, "second": 1.0, "nsecond": 1e-9, "Ghz": 1e9, "Mhz": 1e6, "hz": 1.0}
 
 
