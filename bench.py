@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--resamples", type=int, default=0, help="per GPU per step (c3: per step in total)")
     ap.add_argument("--mapping", default="auto", choices=["auto", "thread", "warp"])
+    ap.add_argument("--schedule", default="auto", choices=["auto", "refill", "rounds"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -298,6 +299,8 @@ def main():
     t_context = time.perf_counter() - t0
     if args.mapping != "auto":
         ctx.set_fit_mapping(args.mapping)
+    if args.schedule != "auto":
+        ctx.set_schedule(args.schedule)
     # the library's own communicator: rank 0's id goes round by torch.distributed, then every
     # all-reduce of the run is fmc_allreduce (one ncclAllReduce on the kernels' stream)
     t0 = time.perf_counter()
@@ -449,7 +452,7 @@ def main():
             "details": {"resamples_per_gpu_per_step": nres, "resamples_per_step": step_ids, "seed": SEED,
                         "jacobian": "forward differences (nl2sno, the reference's path)",
                         "l2": "flushed between steps (256 MiB memset); the data rows live in shared memory",
-                        "geometry": ctx.geometry(),
+                        "geometry": ctx.geometry(), "schedule": ctx.schedule(),
                         "per_fit": {"nfcall": F, "ngcall": G, "niter": tot[2], "passes": tot[3]},
                         "return_codes_3_to_10_last_step": rc[3:11].tolist(),
                         "non_converged_fraction_last_step": float(rc[7:11].sum()) / max(last["nfit"], 1),

@@ -88,6 +88,8 @@ def lib():
     L.fmc_allreduce.argtypes = [C.c_void_p]
     L.fmc_last_combine_method.restype = C.c_int
     L.fmc_set_fit_mapping.argtypes = [C.c_void_p, C.c_int]
+    L.fmc_set_schedule.argtypes = [C.c_void_p, C.c_int]
+    L.fmc_get_schedule.argtypes = [C.c_void_p]
     L.fmc_set_jacobian_mode.argtypes = [C.c_void_p, C.c_int]
     L.fmc_model_has_analytic_jacobian.argtypes = [C.c_int]
     L.fmc_set_histogram.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
@@ -397,6 +399,16 @@ class Context:
         meant for large ndata x nparam -- csrc/warp_kernel.cuh)."""
         code = {"thread": 0, 0: 0, "warp": 1, 1: 1}[mapping]
         _check(lib().fmc_set_fit_mapping(self._h, code), "fmc_set_fit_mapping")
+
+    def set_schedule(self, schedule):
+        """"refill" (one persistent kernel per nl2sno call, threads take the next fit from a counter) or
+        "rounds" (solver steps and passes in separate kernels alternating inside a CUDA graph WHILE node,
+        fits compacted between rounds -- csrc/round_kernels.cuh).  Same per-fit arithmetic."""
+        code = {"refill": 0, 0: 0, "rounds": 1, 1: 1}[schedule]
+        _check(lib().fmc_set_schedule(self._h, code), "fmc_set_schedule")
+
+    def schedule(self):
+        return {0: "refill", 1: "rounds"}[lib().fmc_get_schedule(self._h)]
 
     def set_histogram(self, nbins, lo=None, hi=None):
         """Bin every fitted parameter and property on the device (replaces histogram_<prop>.dat,

@@ -398,70 +398,72 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
     }
   };
 
-  // take the next fit: load its starting point and the sums of its initial pass (stage A),
-  // and run the solver up to its first trial point
-  auto fetch = [&]() {
-    for (;;) {
-      const unsigned long long kk = atomicAdd(a.next_id, 1ULL);
-      if (kk >= (unsigned long long)a.nres) {
-        active = false;
-        return;
-      }
-      slot = (long long)kk;
-      double xs[P];
-      if (a.call == 0) {
+  // take the next fit: load its starting point and the sums of its initial pass (stage A);
+  // false = the work counter of this launch is exhausted
+  auto load_next = [&]() -> bool {
+    const unsigned long long kk = atomicAdd(a.next_id, 1ULL);
+    if (kk >= (unsigned long long)a.nres) return false;
+    slot = (long long)kk;
+    double xs[P];
+    if (a.call == 0) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) xs[i] = a.start[i];
-        s.reset_fit();
-      } else {
+      for (int i = 0; i < P; ++i) xs[i] = a.start[i];
+      s.reset_fit();
+    } else {
 #pragma unroll
-        for (int i = 0; i < P; ++i) xs[i] = a.xbuf[i * a.cap + slot];
-        s.mlstgd = a.istate[slot];
-        s.lsvmin_ix = a.istate[a.cap + slot];
-        s.anomaly = 0;
-      }
-      s.begin(xs);
-      s.res_f = a.init[slot];
-#pragma unroll
-      for (int i = 0; i < P; ++i) s.res_g[i] = a.init[(1 + i) * a.cap + slot];
-#pragma unroll
-      for (int i = 0; i < PP; ++i) s.res_G[i] = a.init[(1 + P + i) * a.cap + slot];
-      fit_passes = 1;
-      active = true;
-      if (s.resume()) {
-        return;
-      }
-      finish_call();  // ended without a single trial step (e.g. residual too big at the start)
+      for (int i = 0; i < P; ++i) xs[i] = a.xbuf[i * a.cap + slot];
+      s.mlstgd = a.istate[slot];
+      s.lsvmin_ix = a.istate[a.cap + slot];
+      s.anomaly = 0;
     }
+    s.begin(xs);
+    s.res_f = a.init[slot];
+#pragma unroll
+    for (int i = 0; i < P; ++i) s.res_g[i] = a.init[(1 + i) * a.cap + slot];
+#pragma unroll
+    for (int i = 0; i < PP; ++i) s.res_G[i] = a.init[(1 + P + i) * a.cap + slot];
+    fit_passes = 1;
+    return true;
   };
-  fetch();
+  active = load_next();
 
+  // The solver step has ONE call site (its inlined code -- tens of KB -- exists once in the kernel;
+  // two copies measurably thrash the 32 KB instruction cache when the fits diverge, C5): on the
+  // first trip every lane consumes the initial sums of its first fit instead of making a pass.
+  bool first_trip = true;
   while (__any_sync(0xffffffffu, active)) {
     if (active) {
-      PassPoint<P> pa, pb;
-      pa.set(s.x, s.hA);   // (the steps are not used by an analytic pass)
-      pb.set(s.x0, s.hJ);
-      PassAcc<P> acc;
-      acc.zero();
-      const unsigned long long id = (unsigned long long)(a.first + slot);
-      const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
-      pass_loop<M, INJECT, true, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
-      if constexpr (JAC == JAC_ANALYTIC)
-        pass_finish_analytic<P>(acc, s);
-      else
-        pass_finish<P>(acc, s);
-      ++fit_passes;
-      bool more = s.resume();
-      if (more && fit_passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
-        s.anomaly |= 8;
-        s.rc = 9;
-        more = false;
+      if (!first_trip) {
+        PassPoint<P> pa, pb;
+        pa.set(s.x, s.hA);   // (the steps are not used by an analytic pass)
+        pb.set(s.x0, s.hJ);
+        PassAcc<P> acc;
+        acc.zero();
+        const unsigned long long id = (unsigned long long)(a.first + slot);
+        const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
+        pass_loop<M, INJECT, true, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
+        if constexpr (JAC == JAC_ANALYTIC)
+          pass_finish_analytic<P>(acc, s);
+        else
+          pass_finish<P>(acc, s);
+        ++fit_passes;
       }
-      if (!more) {
-        finish_call();
-        fetch();
+      for (;;) {
+        bool more = s.resume();
+        if (more && fit_passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
+          s.anomaly |= 8;
+          s.rc = 9;
+          more = false;
+        }
+        if (more) break;
+        finish_call();  // (also a call that ended without a single trial step, e.g. residual too big at the start)
+        if (!load_next()) {
+          active = false;
+          break;
+        }
       }
     }
+    first_trip = false;
   }
   if (a.call == 0) return;
 

@@ -15,6 +15,7 @@
 
 #include "../../include/fmc_b200.h"
 #include "model_registry.cuh"
+#include "round_kernels.cuh"
 #include "warp_kernel.cuh"
 
 // (no `using namespace fmc` here: fmc::exp & co. must not leak into the global scope, where
@@ -36,6 +37,7 @@ namespace {
 thread_local std::string g_last_cuda_error;
 int g_default_jac = 0;  // Jacobian mode of the one-call entry points (fmc_set_jacobian_mode(NULL, .))
 int g_default_mapping = 0;  // fit mapping of the one-call entry points (fmc_set_fit_mapping(NULL, .))
+int g_default_schedule = -1;  // schedule of the one-call entry points (fmc_set_schedule(NULL, .)); -1 = FMC_SCHEDULE env / refill
 
 #define FMC_CUDA(call)                                                                   \
   do {                                                                                   \
@@ -266,6 +268,22 @@ struct fmc_context {
   int comm_nranks = 1;
   int jac = fmc::JAC_FD;  // how Jacobian rows are formed (fmc_set_jacobian_mode)
   int mapping = 0;        // 0 = one fit per thread, 1 = one fit per warp (fmc_set_fit_mapping)
+  int schedule = 0;       // FMC_SCHEDULE_REFILL or FMC_SCHEDULE_ROUNDS (fmc_set_schedule)
+  // ---- round schedule (round_kernels.cuh): slot pool, lists, control words, the WHILE graph
+  fmc::RoundArgs rs{0, nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long rs_state_cap = 0;            // 64-bit words allocated for rs.state
+  long long rs_slot_cap = 0;             // slots allocated for slot_fit / slot_meta / list
+  fmc::KernelArgs* rs_kargs_dev = nullptr;     // the chunk's KernelArgs, read by the graph's kernels
+  fmc::KernelArgs* rs_kargs_pinned = nullptr;  // one per chunk of the launch in flight
+  long long rs_kargs_cap = 0;
+  unsigned int* rs_ctl_pinned = nullptr;
+  cudaStream_t rs_capture_stream = nullptr;
+  cudaGraph_t rs_graph = nullptr;
+  cudaGraphExec_t rs_exec = nullptr;
+  bool rs_no_graph = false;              // FMC_ROUNDS_NO_GRAPH=1 or the graph could not be built: host-driven rounds
+  long long rs_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // what rs_exec was built for
+  long long rs_rounds = 0;               // rounds enqueued by the host-driven fallback
+  bool rs_used = false;                  // the launch in flight ran under the round schedule
   double hist_lo[fmc::HIST_MAX_QUANT] = {0};
   double hist_scale[fmc::HIST_MAX_QUANT] = {0};
   long long rowj_cap = 0;
@@ -277,6 +295,160 @@ struct fmc_context {
   int geom[4] = {0, 0, 0, 0};
   std::vector<RowData> rows_host;
 };
+
+// ---------------------------------------------------------------------------------------
+// Round schedule (round_kernels.cuh): pool allocation, the WHILE graph, one chunk's rounds.
+static int default_schedule() {
+  static const int v = [] {
+    const char* e = std::getenv("FMC_SCHEDULE");
+    return (e && (e[0] == 'r' || e[0] == 'R') && (e[1] == 'o' || e[1] == 'O')) ? FMC_SCHEDULE_ROUNDS
+                                                                                : FMC_SCHEDULE_REFILL;
+  }();
+  return v;
+}
+
+static int rounds_prepare(fmc_context* c, const fmc::RoundEntry& re, int P, bool inject, bool smem, int jac,
+                          size_t shmem, long long cap, long long nchunks) {
+  int bps = 0;
+  FMC_CUDA(re.prepare(inject, smem, jac, shmem, &bps));
+  if (bps < 1) {
+    g_last_cuda_error = "pass kernel does not fit on an SM";
+    return FMC_ERR_CUDA;
+  }
+  // pool: enough slots for several waves of the pass kernel, so that the solve kernel that follows
+  // runs at full occupancy and the partial last wave of a round is a small fraction of it
+  long long waves = 8;
+  if (const char* e = std::getenv("FMC_ROUND_WAVES")) {
+    const long long v = std::atoll(e);
+    if (v >= 1 && v <= 4096) waves = v;
+  }
+  long long slots = (long long)c->num_sms * bps * FMC_ROUND_PASS_THREADS * waves;
+  if (slots > cap) slots = cap;
+  if (slots < 1) slots = 1;
+  c->geom[0] = (int)(slots / FMC_ROUND_PASS_THREADS + 2);
+  c->geom[1] = FMC_ROUND_PASS_THREADS;
+  c->geom[2] = bps;
+  c->geom[3] = c->num_sms;
+  const long long words = (long long)re.state_words * slots;
+  if (words > c->rs_state_cap) {
+    cudaFree(c->rs.state);
+    c->rs.state = nullptr;
+    c->rs_state_cap = 0;
+    FMC_CUDA(cudaMalloc(&c->rs.state, sizeof(unsigned long long) * words));
+    c->rs_state_cap = words;
+  }
+  if (slots > c->rs_slot_cap) {
+    cudaFree(c->rs.slot_fit);
+    cudaFree(c->rs.slot_meta);
+    cudaFree(c->rs.list);
+    c->rs.slot_fit = nullptr;
+    c->rs.slot_meta = nullptr;
+    c->rs.list = nullptr;
+    c->rs_slot_cap = 0;
+    FMC_CUDA(cudaMalloc(&c->rs.slot_fit, sizeof(long long) * slots));
+    FMC_CUDA(cudaMalloc(&c->rs.slot_meta, sizeof(int) * 2 * slots));
+    FMC_CUDA(cudaMalloc(&c->rs.list, sizeof(int) * 4 * slots));
+    c->rs_slot_cap = slots;
+  }
+  if (!c->rs.ctl) {
+    FMC_CUDA(cudaMalloc(&c->rs.ctl, sizeof(unsigned int) * fmc::RC_NWORDS));
+    FMC_CUDA(cudaMalloc(&c->rs_kargs_dev, sizeof(fmc::KernelArgs)));
+    FMC_CUDA(cudaMallocHost(&c->rs_ctl_pinned, sizeof(unsigned int) * fmc::RC_NWORDS));
+    FMC_CUDA(cudaStreamCreateWithFlags(&c->rs_capture_stream, cudaStreamNonBlocking));
+    const char* e = std::getenv("FMC_ROUNDS_NO_GRAPH");
+    c->rs_no_graph = e && e[0] == '1';
+  }
+  if (nchunks > c->rs_kargs_cap) {
+    if (c->rs_kargs_pinned) cudaFreeHost(c->rs_kargs_pinned);
+    c->rs_kargs_pinned = nullptr;
+    c->rs_kargs_cap = 0;
+    FMC_CUDA(cudaMallocHost(&c->rs_kargs_pinned, sizeof(fmc::KernelArgs) * nchunks));
+    c->rs_kargs_cap = nchunks;
+  }
+  c->rs.nslots = slots;
+  FMC_CUDA(cudaMemsetAsync(c->rs.ctl, 0, sizeof(unsigned int) * fmc::RC_NWORDS, c->stream));
+  c->rs_rounds = 0;
+
+  // the WHILE graph: body = one round; rebuilt only when what it was captured for changes
+  const long long key[8] = {c->model, (inject ? 1 : 0) | (smem ? 2 : 0) | (jac << 2), (long long)shmem, slots,
+                            (long long)(size_t)c->rs.state, (long long)(size_t)c->rs.slot_fit,
+                            (long long)(size_t)c->rs.list, (long long)(size_t)c->rs_kargs_dev};
+  (void)P;
+  if (c->rs_no_graph) return FMC_OK;
+  bool same = c->rs_exec != nullptr;
+  for (int i = 0; i < 8; ++i) same = same && key[i] == c->rs_key[i];
+  if (same) return FMC_OK;
+  if (c->rs_exec) cudaGraphExecDestroy(c->rs_exec);
+  if (c->rs_graph) cudaGraphDestroy(c->rs_graph);
+  c->rs_exec = nullptr;
+  c->rs_graph = nullptr;
+  auto give_up = [&](const char* what, cudaError_t e) {
+    // no conditional graph nodes (old driver): host-driven rounds, same kernels
+    g_last_cuda_error = std::string("round graph: ") + what + ": " + cudaGetErrorString(e);
+    if (c->rs_exec) cudaGraphExecDestroy(c->rs_exec);
+    if (c->rs_graph) cudaGraphDestroy(c->rs_graph);
+    c->rs_exec = nullptr;
+    c->rs_graph = nullptr;
+    c->rs_no_graph = true;
+    cudaGetLastError();
+    return FMC_OK;
+  };
+  cudaError_t e = cudaGraphCreate(&c->rs_graph, 0);
+  if (e != cudaSuccess) return give_up("cudaGraphCreate", e);
+  cudaGraphConditionalHandle handle;
+  e = cudaGraphConditionalHandleCreate(&handle, c->rs_graph, 1, cudaGraphCondAssignDefault);
+  if (e != cudaSuccess) return give_up("cudaGraphConditionalHandleCreate", e);
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  e = cudaGraphAddNode(&node, c->rs_graph, nullptr, 0, &np);
+  if (e != cudaSuccess) return give_up("cudaGraphAddNode(conditional)", e);
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  e = cudaStreamBeginCaptureToGraph(c->rs_capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) return give_up("cudaStreamBeginCaptureToGraph", e);
+  e = re.enqueue_round(c->rs_kargs_dev, c->rs, inject, smem, jac, shmem, handle, 1, c->rs_capture_stream);
+  cudaGraph_t captured = nullptr;
+  cudaError_t e2 = cudaStreamEndCapture(c->rs_capture_stream, &captured);
+  if (e != cudaSuccess) return give_up("capture of the round kernels", e);
+  if (e2 != cudaSuccess) return give_up("cudaStreamEndCapture", e2);
+  e = cudaGraphInstantiate(&c->rs_exec, c->rs_graph, 0);
+  if (e != cudaSuccess) return give_up("cudaGraphInstantiate", e);
+  for (int i = 0; i < 8; ++i) c->rs_key[i] = key[i];
+  return FMC_OK;
+}
+
+// The rounds of one chunk: `a` (host copy, pinned, entry ch) is already complete.
+static int rounds_run_chunk(fmc_context* c, const fmc::RoundEntry& re, long long ch, bool inject, bool smem, int jac,
+                            size_t shmem) {
+  FMC_CUDA(cudaMemcpyAsync(c->rs_kargs_dev, &c->rs_kargs_pinned[ch], sizeof(fmc::KernelArgs), cudaMemcpyHostToDevice,
+                           c->stream));
+  // round counter, list lengths and the done flag back to zero (the total keeps counting)
+  FMC_CUDA(cudaMemsetAsync(c->rs.ctl, 0, sizeof(unsigned int) * fmc::RC_ROUNDS_TOTAL, c->stream));
+  if (!c->rs_no_graph) {
+    FMC_CUDA(cudaGraphLaunch(c->rs_exec, c->stream));
+    return FMC_OK;
+  }
+  // host-driven fallback: batches of rounds, the done flag read back between batches (blocks the host)
+  const long long max_rounds = 4LL * (fmc::k::mxfcal + fmc::k::mxiter) + 16;
+  long long done_rounds = 0, batch = 8;
+  while (done_rounds < max_rounds) {
+    for (long long r = 0; r < batch; ++r) {
+      FMC_CUDA(re.enqueue_round(c->rs_kargs_dev, c->rs, inject, smem, jac, shmem, 0, 0, c->stream));
+      ++c->rs_rounds;
+    }
+    done_rounds += batch;
+    FMC_CUDA(cudaMemcpyAsync(c->rs_ctl_pinned, c->rs.ctl, sizeof(unsigned int) * fmc::RC_NWORDS, cudaMemcpyDeviceToHost,
+                             c->stream));
+    FMC_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->rs_ctl_pinned[fmc::RC_DONE] != 0u) return FMC_OK;
+    if (batch < 64) batch *= 2;
+  }
+  g_last_cuda_error = "round schedule: fits still iterating after the cap on rounds";
+  return FMC_ERR_CUDA;
+}
 
 extern "C" {
 
@@ -366,6 +538,7 @@ int fmc_create(fmc_context** out, int device) {
   c->stream = c->own_stream;
   FMC_CUDA(cudaEventCreate(&c->ev0));
   FMC_CUDA(cudaEventCreate(&c->ev1));
+  c->schedule = default_schedule();
   c->acc_n = acc_len(FMC_MAX_PARAM, FMC_MAX_PARAM);
   FMC_CUDA(cudaMalloc(&c->acc_own, sizeof(double) * c->acc_n));
   c->acc = c->acc_own;
@@ -396,6 +569,17 @@ int fmc_destroy(fmc_context* c) {
   cudaFree(c->params_out_dev);
   cudaFree(c->props_out_dev);
   cudaFree(c->counters_dev_out);
+  if (c->rs_exec) cudaGraphExecDestroy(c->rs_exec);
+  if (c->rs_graph) cudaGraphDestroy(c->rs_graph);
+  if (c->rs_capture_stream) cudaStreamDestroy(c->rs_capture_stream);
+  cudaFree(c->rs.state);
+  cudaFree(c->rs.slot_fit);
+  cudaFree(c->rs.slot_meta);
+  cudaFree(c->rs.list);
+  cudaFree(c->rs.ctl);
+  cudaFree(c->rs_kargs_dev);
+  if (c->rs_kargs_pinned) cudaFreeHost(c->rs_kargs_pinned);
+  if (c->rs_ctl_pinned) cudaFreeHost(c->rs_ctl_pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -506,6 +690,17 @@ int fmc_set_fit_mapping(fmc_context* c, int mapping) {
     g_default_mapping = mapping;  // the one-call entry points
   return FMC_OK;
 }
+
+int fmc_set_schedule(fmc_context* c, int schedule) {
+  if (schedule != FMC_SCHEDULE_REFILL && schedule != FMC_SCHEDULE_ROUNDS) return FMC_ERR_BAD_ARG;
+  if (c)
+    c->schedule = schedule;
+  else
+    g_default_schedule = schedule;  // the one-call entry points
+  return FMC_OK;
+}
+
+int fmc_get_schedule(const fmc_context* c) { return c ? c->schedule : g_default_schedule; }
 
 int fmc_model_has_analytic_jacobian(int model) {
   if (model < 0 || model >= fmc_model_count()) return 0;
@@ -721,6 +916,10 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   const int jac = c->jac;
   if (jac == fmc::JAC_ANALYTIC && !m.analytic) return FMC_ERR_BAD_ARG;  // double-only model_y, no model_grad
   const bool per_warp = c->mapping == FMC_FIT_PER_WARP;
+  const bool rounds = !per_warp && c->schedule == FMC_SCHEDULE_ROUNDS;
+  const fmc::RoundEntry rentry = rounds ? fmc::fmc_round_entry(c->model) : fmc::RoundEntry{0, nullptr, nullptr, nullptr};
+  if (rounds && !rentry.enqueue_round) return FMC_ERR_BAD_MODEL;
+  c->rs_used = false;
   const fmc::WarpEntry wentry = per_warp ? fmc::fmc_warp_entry(c->model) : fmc::WarpEntry{nullptr, nullptr, 0};
   fmc::WarpArgs wa;
   std::memset(&wa, 0, sizeof(wa));
@@ -736,6 +935,8 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     wa.n_w = c->n_w;
     shmem = wentry.solver_smem + (wa.stage > 0 ? (wa.stage + m.naux) * col : 0);
     FMC_CUDA(wentry.occupancy(inject, jac, shmem, &bps));
+  } else if (rounds) {
+    bps = 1;  // (the pass kernel's own occupancy is checked in rounds_prepare)
   } else {
     FMC_CUDA(m.occupancy(inject, smem, jac, shmem, &bps));
   }
@@ -777,6 +978,11 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     }
     wa.tscratch = c->tscratch_dev;
   }
+  if (rounds && nresample > 0) {
+    const int prc = rounds_prepare(c, rentry, P, inject, smem, jac, shmem, cap, nchunks);
+    if (prc != FMC_OK) return prc;
+    c->rs_used = true;
+  }
   if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 2 * nchunks, c->stream));
   FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
   FMC_CUDA(cudaMemsetAsync(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP), c->stream));
@@ -806,13 +1012,30 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
       if (wgrid < 1) wgrid = 1;
       grid = wgrid;
     }
-    c->geom[0] = (int)grid;
+    if (!rounds) c->geom[0] = (int)grid;
+    if (rounds) {
+      // round schedule: the first evaluation of the first call for the whole chunk (uniform kernels,
+      // as below), then rounds of solve / pass over the slot pool until every fit of the chunk has
+      // been through both nl2sno calls, then the moment sums
+      a.call = 0;
+      a.next_id = c->counters_dev + 2 * ch;
+      if (shared_init)
+        FMC_LAUNCH(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
+      else
+        FMC_LAUNCH(m.launch_init(a, inject, smem, jac, shmem, c->stream));
+      c->rs_kargs_pinned[ch] = a;
+      const int rrc = rounds_run_chunk(c, rentry, ch, inject, smem, jac, shmem);
+      if (rrc != FMC_OK) return rrc;
+      long long mgrid = (cnt + 255) / 256;
+      if (mgrid > (long long)c->num_sms * 8) mgrid = (long long)c->num_sms * 8;
+      FMC_LAUNCH(rentry.enqueue_moments(c->rs_kargs_dev, (int)mgrid, c->stream));
+    }
     if (per_warp) {
       a.call = 0;
       a.next_id = c->counters_dev + 2 * ch;
       FMC_LAUNCH(wentry.launch(a, wa, inject, jac, (int)grid, shmem, c->stream));
     }
-    for (int call = 0; call < 2 && !per_warp; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
+    for (int call = 0; call < 2 && !per_warp && !rounds; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
       a.call = call;
       a.next_id = c->counters_dev + 2 * ch + call;
       if (call == 0 && shared_init)
@@ -895,7 +1118,19 @@ int fmc_finish(fmc_context* c, double* sum_p, double* sum_p2, double* sum_prop, 
       FMC_CUDA(cudaMemcpyAsync(counters_out, c->counters_dev_out, sizeof(int) * 10 * nres, cudaMemcpyDeviceToHost,
                                c->stream));
   }
+  if (c->rs_used)
+    FMC_CUDA(cudaMemcpyAsync(c->rs_ctl_pinned, c->rs.ctl, sizeof(unsigned int) * fmc::RC_NWORDS, cudaMemcpyDeviceToHost,
+                             c->stream));
   FMC_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->rs_used) {  // three kernels per round (solve, control, pass), counted on the device
+    c->nlaunch += 3LL * c->rs_ctl_pinned[fmc::RC_ROUNDS_TOTAL];
+    c->rs_used = false;
+    if (c->rs_ctl_pinned[fmc::RC_ERROR] != 0u) {
+      c->inflight = -1;
+      g_last_cuda_error = "round schedule: fits still iterating after the cap on rounds";
+      return FMC_ERR_CUDA;
+    }
+  }
   c->inflight = -1;
   long long nfit = 0;
   int rc = fmc_decode_accumulator(c->model, c->start, acc.data(), sum_p, sum_p2, sum_prop, sum_prop2, &nfit,
@@ -1100,6 +1335,7 @@ int bootstrap_run_impl(int model, int ndata, const double* x, const double* y, c
       fmc_set_accumulator_dev(c, nullptr);
       c->jac = g_default_jac;
       c->mapping = g_default_mapping;
+      c->schedule = g_default_schedule >= 0 ? g_default_schedule : default_schedule();
       fmc_set_histogram_dev(c, nullptr);
       if ((rc = fmc_set_histogram(c, nbins, bin_lo, bin_hi)) != FMC_OK) break;  // cached context: also switches off
       if ((rc = fmc_launch(c, params_start, cnt, seed, first_counter + lo, zdev, keep ? 1 : 0)) != FMC_OK) break;
@@ -1220,6 +1456,7 @@ int fmc_fit_once(int model, int ndata, const double* x, const double* y, const d
   fmc_set_histogram(c, 0, nullptr, nullptr);  // the cached context may have binned before
   c->jac = g_default_jac;
   c->mapping = g_default_mapping;
+  c->schedule = g_default_schedule >= 0 ? g_default_schedule : default_schedule();
   rc = fmc_launch(c, params, 1, 0ULL, 0, zdev, 1);
   const int P = models()[model].nparam;
   std::vector<double> pout(P);

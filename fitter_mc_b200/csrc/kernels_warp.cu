@@ -1,7 +1,6 @@
 // Warp-per-fit kernels (warp_kernel.cuh) of the compiled-in models.  Compiled once per model
 // (-DFMC_WARP_MODEL=k, see the Makefile) so that the instantiations build in parallel and the
 // thread-per-fit kernels are compiled exactly as before.
-#define FMC_SOLVER_ROLLED 1  // see nl2_solver.cuh
 #include "models/model_user.cuh"
 #include "models/models_bench.cuh"
 #include "warp_kernel.cuh"

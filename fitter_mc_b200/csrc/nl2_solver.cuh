@@ -322,13 +322,14 @@ FMC_HD void Nl2<P>::factor() {
   {
     int m = 0;
     FMC_SOLVER_LOOP
-    for (int i = 0; i < P; ++i)
+    for (int i = 0; i < P; ++i) {
       FMC_SOLVER_LOOP
       for (int j = 0; j <= i; ++j) {
         A[i][j] = G[m];
         A[j][i] = G[m];
         ++m;
       }
+    }
   }
   FMC_SOLVER_LOOP
   for (int j = 0; j < P; ++j) ipivot[j] = j + 1;
@@ -380,13 +381,14 @@ FMC_HD void Nl2<P>::factor() {
     FMC_SOLVER_LOOP
     for (int j = kk + 1; j < P; ++j) FMC_R(kk, j) = A[kk][j] / rkk;
     FMC_SOLVER_LOOP
-    for (int i = kk + 1; i < P; ++i)
+    for (int i = kk + 1; i < P; ++i) {
       FMC_SOLVER_LOOP
       for (int j = i; j < P; ++j) {
         double t = A[i][j] - FMC_R(kk, i) * FMC_R(kk, j);
         A[i][j] = t;
         A[j][i] = t;
       }
+    }
   }
   // qtr = R^-T P^T g on the leading `rank` rows
   FMC_SOLVER_LOOP

@@ -1,0 +1,424 @@
+// Round-synchronous schedule of the bootstrap fits ("convergence mask + compaction" at the
+// grid level; the alternative to the refill kernel of bootstrap_kernel.cuh, chosen by measurement
+// per workload -- DESIGN.md section 2.8).
+//
+// Replaces the same reference code as iterate_kernel (bootstrap.f90:309-327, fit_data 215-226 and
+// everything nl2sno calls), with the work of one fit split between two kernels that alternate:
+//
+//   round_solve_kernel   one thread per SLOT of a pool of C slots: consumes the sums of the pass just
+//                        made (Nl2::resume -- assess, model switch, secant update, the next
+//                        Levenberg-Marquardt / gqtstp step), and either asks for another pass or
+//                        ends the nl2sno call.  A fit whose FIRST call ends continues in place with
+//                        the second (bootstrap.f90:222-225); a fit whose second call ends hands its
+//                        slot to the next fit of the chunk (work counter).  Slots that want a pass
+//                        are appended to one of two lists: with the J(x0)^T r(x) part (every trial
+//                        pass) or without (the first pass of the second call).
+//   round_ctl_kernel     one thread: publishes the list lengths, clears the other pair of lists,
+//                        and tells the CUDA graph's WHILE node whether another round is needed.
+//   round_pass_kernel    one thread per list entry: the streaming pass over the n data points
+//                        (pass_loop, identical arithmetic to the refill kernel), nothing else.
+//
+// Why: in the refill kernel the p x p solver step runs with 8 warps per SM whose lanes take
+// different branches of ~100 KB of inlined code.  For well-behaved fits (C1, C2) that costs ~15 %;
+// for the stress config C5 (23 % non-converging fits, 77 passes per fit) ncu shows 2.5 of 32 lanes
+// active in the solver code, 4.2 "no instruction" stall cycles per issued instruction -- the
+// solver's code evicts the pass loop from the 32 KB instruction cache -- and an FP64 pipe 30 % busy
+// (profiles/r2_ncu_c5_summary.txt).  Here the pass kernel is 12 KB of straight-line code with all 32
+// lanes busy, and the divergent solver code runs at full occupancy where its latencies overlap.
+// Cost: the solver state (sizeof(Nl2<P>): 1.7 KB for p = 4) makes a round trip through HBM/L2 per
+// pass, ~3.4 KB per fit and pass against ~190 000 instructions of pass work at n = 1000.
+//
+// The per-fit arithmetic is the refill kernel's, operation for operation (same pass_loop, same
+// resume()), so a fit's result does not depend on the schedule (tests/test_round_schedule.py).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "model_registry.cuh"
+
+namespace fmc {
+
+#ifndef FMC_ROUND_SOLVE_THREADS
+#define FMC_ROUND_SOLVE_THREADS 128
+#endif
+// Pass kernel: blocks of 128 threads.  Without the solver's state the row loop of a p <= 4 model
+// needs ~160 registers and no stack (ptxas), so three blocks = 12 warps fit on an SM where the refill
+// kernel has 8; p = 10 needs all 255 registers and gets two blocks.
+#ifndef FMC_ROUND_PASS_THREADS
+#define FMC_ROUND_PASS_THREADS 128
+#endif
+
+// ctl words
+enum { RC_ROUND = 0, RC_COUNTS = 1, RC_DONE = 5, RC_ROUNDS_TOTAL = 6, RC_ERROR = 7, RC_NWORDS = 8 };  // counts: [parity][kind]
+
+struct RoundArgs {
+  long long nslots;            // C: slots of the pool
+  unsigned long long* state;   // [W][C]   solver state images (Nl2<P> as 64-bit words), word-major
+  long long* slot_fit;         // [C]      chunk-local index of the fit in the slot, < 0 = idle
+  int* slot_meta;              // [2][C]   0 = nl2sno call of fit_data the fit is in, 1 = passes of that call so far
+  int* list;                   // [2][2][C] slots that want a pass: [parity of the round][with B, without][.]
+  unsigned int* ctl;           // [RC_NWORDS]
+};
+
+template <int P>
+constexpr int state_words() {
+  return (int)((sizeof(Nl2<P>) + 7) / 8);
+}
+
+// The evaluation points and the pass results are the leading members of Nl2<P>, so the pass kernel
+// reads and writes them in place inside the state image (no second copy of them anywhere).
+template <int P>
+struct StateLayout {
+  static constexpr int PP = P * (P + 1) / 2;
+  static constexpr int X = 0, HA = P, X0 = 2 * P, HJ = 3 * P, RES_F = 4 * P, RES_G = 4 * P + 1,
+                       RES_GG = 5 * P + 1, RES_LKY = 5 * P + 1 + PP;
+  static_assert(offsetof(Nl2<P>, x) == 8 * X && offsetof(Nl2<P>, hA) == 8 * HA && offsetof(Nl2<P>, x0) == 8 * X0 &&
+                    offsetof(Nl2<P>, hJ) == 8 * HJ && offsetof(Nl2<P>, res_f) == 8 * RES_F &&
+                    offsetof(Nl2<P>, res_g) == 8 * RES_G && offsetof(Nl2<P>, res_G) == 8 * RES_GG &&
+                    offsetof(Nl2<P>, res_lky) == 8 * RES_LKY,
+                "round_pass_kernel addresses these members by word offset");
+};
+
+// ---------------------------------------------------------------------------------------
+template <class M, int JAC>
+__global__ void __launch_bounds__(FMC_ROUND_SOLVE_THREADS) round_solve_kernel(const KernelArgs* __restrict__ ap,
+                                                                              const RoundArgs ra) {
+  constexpr int P = M::NPARAM;
+  constexpr int PP = P * (P + 1) / 2;
+  constexpr int W = (int)((sizeof(Nl2<P>) + 7) / 8);  // state_words<P>()
+  const long long C = ra.nslots;
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= C) return;
+  const unsigned int round = ra.ctl[RC_ROUND];
+  long long fit = round == 0 ? -1 : ra.slot_fit[slot];  // round 0 of a chunk: every slot takes a fit
+  if (round != 0 && fit < 0) return;                    // idle slot (the chunk is draining)
+
+  const long long cap = ap->cap, nres = ap->nres;
+  union Image {
+    Nl2<P> s;
+    unsigned long long w[W];
+    __device__ Image() {}
+  } im;
+  Nl2<P>& s = im.s;
+  int call = 0, fit_passes = 0;
+  bool have = false;
+  if (fit >= 0) {
+#pragma unroll 4
+    for (int w = 0; w < W; ++w) im.w[w] = ra.state[(long long)w * C + slot];
+    call = ra.slot_meta[slot];
+    fit_passes = ra.slot_meta[C + slot] + 1;  // the pass whose sums are in the image
+    have = true;
+  }
+  for (;;) {
+    if (have) {
+      bool more = s.resume();
+      if (more && fit_passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
+        s.anomaly |= 8;
+        s.rc = 9;
+        more = false;
+      }
+      if (more) break;
+      // ---- end of an nl2sno call
+      if (s.anomaly != 0 && ap->anom != nullptr) {
+        const unsigned long long kk = atomicAdd(ap->anom, 1ULL);
+        if (kk < (unsigned long long)ANOM_CAP) {
+          ap->anom[1 + 2 * kk] = (unsigned long long)(ap->first + fit);
+          ap->anom[2 + 2 * kk] = (unsigned long long)(s.anomaly | (call << 8));
+        }
+        s.anomaly = 0;
+      }
+      int* cnt = ap->cnt + (size_t)(5 * call) * cap + fit;
+      cnt[0 * cap] = s.rc;
+      cnt[1 * cap] = s.nfcall;
+      cnt[2 * cap] = s.ngcall;
+      cnt[3 * cap] = s.niter;
+      cnt[4 * cap] = fit_passes;
+      if (call == 0) {
+        // fit_data calls nl2sno a second time from the answer of the first (bootstrap.f90:222-225):
+        // the fit stays in its slot; iv(mlstgd) and lsvmin's generator carry over as in the reference
+        double xs[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) xs[i] = s.x[i];
+        s.begin(xs);
+        call = 1;
+        fit_passes = 0;
+        break;  // wants the first evaluation of the call: residual + Jacobian at x, D = 1, no x0 part
+      }
+#pragma unroll
+      for (int i = 0; i < P; ++i) ap->xbuf[(size_t)i * cap + fit] = s.x[i];
+      have = false;
+    }
+    // ---- take the next fit of the chunk: starting point + the sums of its initial pass (stage A)
+    const unsigned long long kk = atomicAdd(ap->next_id, 1ULL);
+    if (kk >= (unsigned long long)nres) {
+      ra.slot_fit[slot] = -1;
+      return;
+    }
+    fit = (long long)kk;
+    double xs[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) xs[i] = ap->start[i];
+    s.reset_fit();
+    s.begin(xs);
+    s.res_f = ap->init[fit];
+#pragma unroll
+    for (int i = 0; i < P; ++i) s.res_g[i] = ap->init[(size_t)(1 + i) * cap + fit];
+#pragma unroll
+    for (int i = 0; i < PP; ++i) s.res_G[i] = ap->init[(size_t)(1 + P + i) * cap + fit];
+    call = 0;
+    fit_passes = 1;
+    have = true;
+  }
+  // ---- another pass is wanted: park the state, queue the slot
+#pragma unroll 4
+  for (int w = 0; w < W; ++w) ra.state[(long long)w * C + slot] = im.w[w];
+  ra.slot_fit[slot] = fit;
+  ra.slot_meta[slot] = call;
+  ra.slot_meta[C + slot] = fit_passes;
+  const unsigned int par = round & 1u;
+  const unsigned int kind = s.need_b ? 0u : 1u;
+  const unsigned int pos = atomicAdd(&ra.ctl[RC_COUNTS + 2 * par + kind], 1u);
+  ra.list[(size_t)(2 * par + kind) * C + pos] = (int)slot;
+}
+
+// ---------------------------------------------------------------------------------------
+// One thread.  `handle` is the WHILE node's condition when the rounds run inside a CUDA graph
+// (use_handle != 0); the host-driven fallback reads ctl instead.
+template <class M>  // (a template only so that the header can be included by several translation units)
+__global__ void round_ctl_kernel(const RoundArgs ra, cudaGraphConditionalHandle handle, int use_handle) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned int round = ra.ctl[RC_ROUND];
+  const unsigned int par = round & 1u;
+  unsigned int n = ra.ctl[RC_COUNTS + 2 * par] + ra.ctl[RC_COUNTS + 2 * par + 1];
+  // a chunk needs at most (passes per call cap) x 2 calls rounds; whatever happens, the loop ends
+  const bool runaway = n != 0u && round > 4u * (unsigned int)(k::mxfcal + k::mxiter) + 16u;
+  if (runaway) {
+    n = 0u;
+    ra.ctl[RC_ERROR] = 1u;
+  }
+  ra.ctl[RC_COUNTS + 2 * (par ^ 1u)] = 0u;
+  ra.ctl[RC_COUNTS + 2 * (par ^ 1u) + 1] = 0u;
+  ra.ctl[RC_ROUND] = round + 1u;
+  ra.ctl[RC_DONE] = n == 0u ? 1u : 0u;
+  ra.ctl[RC_ROUNDS_TOTAL] += 1u;
+  if (use_handle) cudaGraphSetConditional(handle, n != 0u ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------
+template <class M, bool INJECT, bool SMEM, int JAC>
+__global__ void __launch_bounds__(FMC_ROUND_PASS_THREADS, (M::NPARAM <= 6 ? 3 : 2)) round_pass_kernel(const KernelArgs* __restrict__ ap,
+                                                                                 const RoundArgs ra) {
+  constexpr int P = M::NPARAM;
+  constexpr int PP = P * (P + 1) / 2;
+  using L = StateLayout<P>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long C = ra.nslots;
+  const unsigned int par = (ra.ctl[RC_ROUND] - 1u) & 1u;  // (the control kernel has advanced the counter)
+  const unsigned int nA = ra.ctl[RC_COUNTS + 2 * par], nN = ra.ctl[RC_COUNTS + 2 * par + 1];
+  const unsigned int blocksA = (nA + FMC_ROUND_PASS_THREADS - 1) / FMC_ROUND_PASS_THREADS;
+  // blocks [0, blocksA) take the list "with B", the following ones the list "without"; the rest exit
+  const bool with_b = blockIdx.x < blocksA;
+  const unsigned int b = with_b ? blockIdx.x : blockIdx.x - blocksA;
+  const unsigned int cnt = with_b ? nA : nN;
+  if ((unsigned long long)b * FMC_ROUND_PASS_THREADS >= cnt) return;
+  const KernelArgs a = *ap;
+  const double* aux = nullptr;
+  const RowData* rows = stage_rows<SMEM, model_naux<M>::value>(a, smem_raw, &aux);
+  const unsigned int idx = b * FMC_ROUND_PASS_THREADS + threadIdx.x;
+  if (idx >= cnt) return;
+  const long long slot = ra.list[(size_t)(2 * par + (with_b ? 0 : 1)) * C + idx];
+  double* img = reinterpret_cast<double*>(ra.state) + slot;  // word w of the image: img[w * C]
+  double x[P], h[P], x0[P], h0[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    x[i] = img[(long long)(L::X + i) * C];
+    h[i] = img[(long long)(L::HA + i) * C];
+    x0[i] = img[(long long)(L::X0 + i) * C];
+    h0[i] = img[(long long)(L::HJ + i) * C];
+  }
+  PassPoint<P> pa, pb;
+  pa.set(x, h);
+  pb.set(x0, h0);
+  PassAcc<P> acc;
+  acc.zero();
+  const long long fit = ra.slot_fit[slot];
+  const unsigned long long id = (unsigned long long)(a.first + fit);
+  const double* zrow = INJECT ? a.z_inject + (unsigned long long)fit * a.n : nullptr;
+  if (with_b)
+    pass_loop<M, INJECT, true, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
+  else
+    pass_loop<M, INJECT, false, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
+  double f, g[P], G[PP], lky[P];
+  if constexpr (JAC == JAC_ANALYTIC) {
+    f = acc.f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      g[i] = acc.g[i];
+      lky[i] = acc.lky[i];
+    }
+#pragma unroll
+    for (int i = 0; i < PP; ++i) G[i] = acc.G[i];
+  } else {
+    pass_scale<P>(acc, h, h0, f, g, G, lky);
+  }
+  img[(long long)L::RES_F * C] = f;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    img[(long long)(L::RES_G + i) * C] = g[i];
+    img[(long long)(L::RES_LKY + i) * C] = lky[i];
+  }
+#pragma unroll
+  for (int i = 0; i < PP; ++i) img[(long long)(L::RES_GG + i) * C] = G[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// After the rounds of a chunk: derived properties, compensated moment sums of shifted values,
+// optional per-resample outputs, return-code histogram and counters (bootstrap.f90:316-318),
+// from the per-fit results the solve kernel left in xbuf / cnt.  Fits are dealt to threads by
+// index, so a thread's sums do not depend on the order in which the fits finished.
+template <class M>
+__global__ void __launch_bounds__(256) round_moments_kernel(const KernelArgs* __restrict__ ap) {
+  constexpr int P = M::NPARAM;
+  constexpr int Q = M::NPROP;
+  constexpr int NM = 2 * (P + Q);
+  __shared__ double red[256 / 32];
+  __shared__ unsigned int sh_rc[16];
+  if (threadIdx.x < 16) sh_rc[threadIdx.x] = 0u;
+  __syncthreads();
+  const KernelArgs& a = *ap;
+  const long long cap = a.cap, nres = a.nres;
+  double msum[NM], mcmp[NM];
+#pragma unroll
+  for (int i = 0; i < NM; ++i) {
+    msum[i] = 0.0;
+    mcmp[i] = 0.0;
+  }
+  double cq[Q > 0 ? Q : 1];
+  M::derived_properties(a.start, cq);
+  unsigned int n_fit = 0, n_fcall = 0, n_gcall = 0, n_iter = 0, n_pass = 0;
+  for (long long fit = (long long)blockIdx.x * blockDim.x + threadIdx.x; fit < nres;
+       fit += (long long)gridDim.x * blockDim.x) {
+    double x[P], props[Q > 0 ? Q : 1];
+#pragma unroll
+    for (int i = 0; i < P; ++i) x[i] = a.xbuf[(size_t)i * cap + fit];
+    M::derived_properties(x, props);  // bootstrap.f90:316
+#pragma unroll
+    for (int i = 0; i < P; ++i) {     // bootstrap.f90:317-318, on shifted values
+      const double dv = x[i] - a.start[i];
+      kahan_add(msum[i], mcmp[i], dv);
+      kahan_add(msum[P + i], mcmp[P + i], dv * dv);
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const double dv = props[i] - cq[i];
+      kahan_add(msum[2 * P + i], mcmp[2 * P + i], dv);
+      kahan_add(msum[2 * P + Q + i], mcmp[2 * P + Q + i], dv * dv);
+    }
+    int c[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) c[i] = a.cnt[(size_t)i * cap + fit];
+    ++n_fit;
+    n_fcall += c[1] + c[6];
+    n_gcall += c[2] + c[7];
+    n_iter += c[3] + c[8];
+    n_pass += c[4] + c[9];
+    atomicAdd(&sh_rc[c[5] & 15], 1u);
+    if (a.params_out)
+      for (int i = 0; i < P; ++i) a.params_out[fit * P + i] = x[i];
+    if (a.props_out)
+      for (int i = 0; i < Q; ++i) a.props_out[fit * Q + i] = props[i];
+    if (a.counters_out)
+      for (int i = 0; i < 10; ++i) a.counters_out[fit * 10 + i] = c[i];
+  }
+  auto block_sum = [&](double v) -> double {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+      for (int w = 0; w < 256 / 32; ++w) t += red[w];
+    return t;
+  };
+#pragma unroll 1
+  for (int i = 0; i < NM; ++i) {
+    const double t = block_sum(msum[i] - mcmp[i]);
+    if (threadIdx.x == 0) atomicAdd(&a.acc[i], t);
+  }
+  const double tails[5] = {(double)n_fit, (double)n_fcall, (double)n_gcall, (double)n_iter, (double)n_pass};
+  const int tail_idx[5] = {ACC_NFIT, ACC_NFCALL, ACC_NGCALL, ACC_NITER, ACC_NPASS};
+#pragma unroll 1
+  for (int i = 0; i < 5; ++i) {
+    const double t = block_sum(tails[i]);
+    if (threadIdx.x == 0) atomicAdd(&a.acc[NM + tail_idx[i]], t);
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && sh_rc[threadIdx.x] != 0u)
+    atomicAdd(&a.acc[NM + ACC_RC + threadIdx.x], (double)sh_rc[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------
+// Host-side binding of one model to its round-kernel instantiations (kernels_round.cu).
+struct RoundEntry {
+  int state_words;  // 64-bit words of one solver state image
+  // enqueue one round (solve, control, pass) on `st` -- inside a stream capture or directly
+  cudaError_t (*enqueue_round)(const KernelArgs* ap, const RoundArgs& ra, bool inject, bool smem, int jac,
+                               size_t shmem, cudaGraphConditionalHandle handle, int use_handle, cudaStream_t st);
+  cudaError_t (*enqueue_moments)(const KernelArgs* ap, int grid, cudaStream_t st);
+  cudaError_t (*prepare)(bool inject, bool smem, int jac, size_t shmem, int* pass_blocks_per_sm);
+};
+
+template <class M>
+struct RoundBinding {
+  using MB = ModelBinding<M>;
+  static cudaError_t enqueue_round(const KernelArgs* ap, const RoundArgs& ra, bool inject, bool smem, int jac,
+                                   size_t shmem, cudaGraphConditionalHandle handle, int use_handle,
+                                   cudaStream_t st) {
+    const unsigned int sgrid = (unsigned int)((ra.nslots + FMC_ROUND_SOLVE_THREADS - 1) / FMC_ROUND_SOLVE_THREADS);
+    // both lists together hold at most C slots: ceil(nA/T) + ceil(nN/T) <= C/T + 2 blocks
+    const unsigned int pgrid = (unsigned int)(ra.nslots / FMC_ROUND_PASS_THREADS + 2);
+    return MB::dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
+      round_solve_kernel<M, decltype(J)::value><<<sgrid, FMC_ROUND_SOLVE_THREADS, 0, st>>>(ap, ra);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      round_ctl_kernel<M><<<1, 32, 0, st>>>(ra, handle, use_handle);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      round_pass_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>
+          <<<pgrid, FMC_ROUND_PASS_THREADS, shmem, st>>>(ap, ra);
+      return cudaGetLastError();
+    });
+  }
+  static cudaError_t enqueue_moments(const KernelArgs* ap, int grid, cudaStream_t st) {
+    round_moments_kernel<M><<<grid, 256, 0, st>>>(ap);
+    return cudaGetLastError();
+  }
+  static cudaError_t prepare(bool inject, bool smem, int jac, size_t shmem, int* nb) {
+    return MB::dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
+      auto kern = round_pass_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+      if (e != cudaSuccess) return e;
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, kern, FMC_ROUND_PASS_THREADS, shmem);
+    });
+  }
+  static RoundEntry entry() { return RoundEntry{state_words<M::NPARAM>(), enqueue_round, enqueue_moments, prepare}; }
+};
+
+// kernels_round.cu, one object per model
+RoundEntry fmc_round_entry_model0();
+RoundEntry fmc_round_entry_model1();
+RoundEntry fmc_round_entry_model2();
+RoundEntry fmc_round_entry_model3();
+inline RoundEntry fmc_round_entry(int model) {
+  switch (model) {
+    case 0: return fmc_round_entry_model0();
+    case 1: return fmc_round_entry_model1();
+    case 2: return fmc_round_entry_model2();
+    case 3: return fmc_round_entry_model3();
+  }
+  return RoundEntry{0, nullptr, nullptr, nullptr};
+}
+
+}  // namespace fmc

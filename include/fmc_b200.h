@@ -188,6 +188,19 @@ int fmc_model_has_analytic_jacobian(int model);
 #define FMC_FIT_PER_WARP 1
 int fmc_set_fit_mapping(fmc_context* ctx, int mapping);
 
+/* ---- how the iterations of the fits are scheduled ----------------------------------------
+ * FMC_SCHEDULE_REFILL: one persistent kernel per nl2sno call; a thread runs passes and solver
+ * steps of its fit and takes the next fit from a counter when it ends.
+ * FMC_SCHEDULE_ROUNDS: passes and solver steps in separate kernels that alternate inside a CUDA
+ * graph WHILE node; fits that want another pass are compacted into lists between rounds
+ * (DESIGN.md 2.8).  Same per-fit arithmetic, bit for bit; which one is faster depends on how
+ * much the fits diverge (measured: DESIGN.md 2.8).  The default is FMC_SCHEDULE_REFILL unless the
+ * environment variable FMC_SCHEDULE=rounds is set.  ctx = NULL sets it for the one-call entry points. */
+#define FMC_SCHEDULE_REFILL 0
+#define FMC_SCHEDULE_ROUNDS 1
+int fmc_set_schedule(fmc_context* ctx, int schedule);
+int fmc_get_schedule(const fmc_context* ctx);
+
 /* ---- binned distributions -------------------------------------------
  * Replaces the reference's histogram_<prop>.dat dumps -- one list-directed text line per
  * resample and property, written inside an OMP CRITICAL (bootstrap.f90:301-308, 319-325,

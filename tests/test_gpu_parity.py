@@ -7,9 +7,13 @@ reference algorithm itself, compiled at the reference's own default flags (-Ofas
 -march=native) versus strict IEEE, differs per fit by a median of 1e-9..4e-9, a 99th
 percentile of 5e-8 and a maximum of 7e-8 (forward-difference noise decides whether the last
 noise-level step of the second nl2sno call is accepted), so 1e-9 is below the reference's own
-reproducibility floor.  The tolerances asserted here are therefore:
-   median rel. deviation <= 1e-8, max rel. deviation <= 5e-7, max deviation <= 1e-4 sigma,
-and the measured distribution is printed so it can be compared with that floor.
+reproducibility floor.  profiles/r2_parity_attribution.txt attributes the tail fit by fit: fits whose
+solver takes the same decisions as the oracle's agree to 2e-9 (1e-16 with exact derivatives on both
+sides); every fit beyond 1e-8 has a flipped decision in the noise-level last step of the second
+call (stop test, or keep / restore x in assess, toms573.f90:1905-1948), with or without
+perturbation arithmetic.  The tolerances asserted here are the measured floor:
+   median rel. deviation <= 5e-9, max rel. deviation <= 1e-7, max deviation <= 1e-4 sigma,
+and the measured distribution (with the fraction within 1e-9) is printed.
 """
 import numpy as np
 import pytest
@@ -18,7 +22,7 @@ import datasets
 
 pytestmark = pytest.mark.gpu
 
-REL_MEDIAN, REL_MAX, SIGMA_MAX = 1e-8, 5e-7, 1e-4
+REL_MEDIAN, REL_MAX, SIGMA_MAX = 5e-9, 1e-7, 1e-4
 
 
 @pytest.fixture(scope="module")

@@ -1,0 +1,128 @@
+"""The round schedule (csrc/round_kernels.cuh: solver steps and passes in separate kernels alternating
+inside a CUDA graph WHILE node, fits compacted between rounds) against the refill schedule
+(csrc/bootstrap_kernel.cuh) and the oracle.  Both schedules run the same pass_loop and the same
+Nl2::resume per fit, so per-fit results must be IDENTICAL, bit for bit, whatever the pool size,
+the chunking or the way the rounds are driven (graph or host loop)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import datasets
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_schedule_argument_checks():
+    import fitter_mc_b200 as fmc
+
+    L = fmc.lib()
+    assert L.fmc_set_schedule(None, 7) == -4
+    assert L.fmc_set_schedule(None, 1) == 0 and L.fmc_get_schedule(None) == 1
+    assert L.fmc_set_schedule(None, 0) == 0 and L.fmc_get_schedule(None) == 0
+
+
+def _start(oracle, name, model, x, y, err):
+    if name == "c5":
+        return datasets.C5_FITTED.copy()
+    return oracle.fit_data(model, x, y, err, oracle.model_info(model)["params_init"])[0]
+
+
+def _run(fmc, schedule, model, x, y, err, start, nres, z=None, first=0, jac="fd"):
+    import torch
+
+    ctx = fmc.Context(0)
+    try:
+        ctx.set_data(model, x, y, err)
+        ctx.set_schedule(schedule)
+        ctx.set_jacobian_mode(jac)
+        zdev = None
+        if z is not None:
+            zdev = torch.from_numpy(np.ascontiguousarray(z)).cuda()
+            torch.cuda.synchronize()
+        ctx.launch(start, nres, first_counter=first, z_inject_dev=zdev.data_ptr() if zdev is not None else None,
+                   keep=True)
+        out = ctx.finish()
+        out["launches"] = ctx.launch_count()
+        out["anomalies"] = ctx.anomalies()[2]
+        return out
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nres,inject", [("c1", 5000, False), ("c2", 3000, False), ("c2", 1024, True),
+                                              ("c2p3", 2000, False), ("c5mild", 2000, False), ("c4", 600, False),
+                                              ("c5", 3000, False)])
+def test_rounds_and_refill_give_identical_fits(oracle, name, nres, inject):
+    import fitter_mc_b200 as fmc
+
+    model, x, y, err = datasets.dataset(name)
+    start = _start(oracle, name, model, x, y, err)
+    z = np.random.default_rng(7).normal(size=(nres, len(x))) if inject else None
+    a = _run(fmc, "refill", model, x, y, err, start, nres, z)
+    b = _run(fmc, "rounds", model, x, y, err, start, nres, z)
+    assert np.array_equal(a["params"], b["params"])
+    assert np.array_equal(a["props"], b["props"])
+    assert np.array_equal(a["counters"], b["counters"])          # return codes, evaluations, iterations, passes
+    assert np.array_equal(a["rc_count"], b["rc_count"]) and np.array_equal(a["totals"], b["totals"])
+    assert np.allclose(a["sum_p"], b["sum_p"], rtol=1e-12) and np.allclose(a["sum_p2"], b["sum_p2"], rtol=1e-12)
+    assert np.allclose(a["sum_prop"], b["sum_prop"], rtol=1e-12)
+    assert np.allclose(b["sum_p"], b["params"].sum(0), rtol=1e-9)
+    assert a["anomalies"] == b["anomalies"]
+    print("\n[rounds %s] %d fits identical; kernels launched: refill %d, rounds %d" % (name, nres, a["launches"], b["launches"]))
+
+
+@pytest.mark.gpu
+def test_rounds_analytic_mode_and_small_pool_and_host_driven_rounds(oracle):
+    """Exact-Jacobian mode under the round schedule; a pool much smaller than the chunk (every slot is
+    refilled many times); rounds driven by the host instead of the graph's WHILE node (FMC_ROUNDS_NO_GRAPH=1,
+    the fallback for drivers without conditional graph nodes).  Each in a fresh process (environment)."""
+    code = r"""
+import sys, json, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import datasets, oracle_lib as oracle, fitter_mc_b200 as fmc
+model, x, y, err = datasets.dataset("c2")
+start = oracle.fit_data(model, x, y, err, oracle.model_info(model)["params_init"])[0]
+out = {}
+for sched in ("refill", "rounds"):
+    for jac in ("fd", "analytic"):
+        ctx = fmc.Context(0); ctx.set_data(model, x, y, err); ctx.set_schedule(sched); ctx.set_jacobian_mode(jac)
+        ctx.launch(start, 40000, first_counter=123, keep=True); r = ctx.finish()
+        out[sched + "/" + jac] = [r["params"].tobytes().hex()[:64], float(r["sum_p"][0]), int(r["counters"].sum()),
+                                  __import__("hashlib").sha256(r["params"].tobytes()).hexdigest(), ctx.launch_count()]
+        ctx.close()
+print(json.dumps(out))
+""" % dict(root=ROOT)
+    res = {}
+    for tag, env in (("graph", {}), ("small-pool", {"FMC_ROUND_WAVES": "1"}), ("host-driven", {"FMC_ROUNDS_NO_GRAPH": "1"})):
+        e = dict(os.environ)
+        e.update(env)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[tag] = __import__("json").loads(p.stdout.strip().splitlines()[-1])
+    ref = res["graph"]
+    for tag, r in res.items():
+        for jac in ("fd", "analytic"):
+            assert r["rounds/" + jac][3] == ref["refill/" + jac][3], (tag, jac)   # same fits, bit for bit
+            assert r["rounds/" + jac][2] == ref["refill/" + jac][2]
+    assert ref["refill/fd"][3] != ref["refill/analytic"][3]
+    print("\n[rounds] launches: %s" % {t: r["rounds/fd"][4] for t, r in res.items()})
+
+
+@pytest.mark.gpu
+def test_rounds_per_fit_parity_with_the_oracle(oracle):
+    import fitter_mc_b200 as fmc
+
+    model, x, y, err = datasets.dataset("c2")
+    start = _start(oracle, "c2", model, x, y, err)
+    nres = 1024
+    z = np.random.default_rng(2024).normal(size=(nres, len(x)))
+    got = _run(fmc, "rounds", model, x, y, err, start, nres, z)
+    want = oracle.bootstrap(model, x, y, err, start, nres, z=z, nthreads=8)
+    rel = (np.abs(got["params"] - want["params"]) / np.abs(want["params"])).max(1)
+    print("\n[rounds parity c2] median %.2e p99 %.2e max %.2e" % (np.median(rel), np.quantile(rel, 0.99), rel.max()))
+    assert np.median(rel) <= 5e-9 and rel.max() <= 1e-7
+    assert np.allclose(got["sum_p"], want["sum_p"], rtol=1e-9)
