@@ -432,34 +432,43 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
   // first trip every lane consumes the initial sums of its first fit instead of making a pass.
   bool first_trip = true;
   while (__any_sync(0xffffffffu, active)) {
-    if (active) {
-      if (!first_trip) {
-        PassPoint<P> pa, pb;
-        pa.set(s.x, s.hA);   // (the steps are not used by an analytic pass)
-        pb.set(s.x0, s.hJ);
-        PassAcc<P> acc;
-        acc.zero();
-        const unsigned long long id = (unsigned long long)(a.first + slot);
-        const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
-        pass_loop<M, INJECT, true, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
-        if constexpr (JAC == JAC_ANALYTIC)
-          pass_finish_analytic<P>(acc, s);
-        else
-          pass_finish<P>(acc, s);
-        ++fit_passes;
-      }
-      for (;;) {
-        bool more = s.resume();
+    if (active && !first_trip) {
+      PassPoint<P> pa, pb;
+      pa.set(s.x, s.hA);   // (the steps are not used by an analytic pass)
+      pb.set(s.x0, s.hJ);
+      PassAcc<P> acc;
+      acc.zero();
+      const unsigned long long id = (unsigned long long)(a.first + slot);
+      const double* zrow = INJECT ? a.z_inject + (unsigned long long)slot * a.n : nullptr;
+      pass_loop<M, INJECT, true, JAC>(rows, aux, a.n, a.n_pad, a.seed, id, zrow, pa, pb, acc);
+      if constexpr (JAC == JAC_ANALYTIC)
+        pass_finish_analytic<P>(acc, s);
+      else
+        pass_finish<P>(acc, s);
+      ++fit_passes;
+    }
+    // ---- the solver step of every lane that has just made a pass (or taken its first fit), and of
+    // the lanes whose fit ended and that took another one: the lanes that call resume() together pass
+    // their mask, so that the routine can keep them converged (nl2_solver.cuh)
+    bool need = active;
+    for (;;) {
+      const unsigned int lanes = __ballot_sync(0xffffffffu, need);
+      if (lanes == 0u) break;
+      if (need) {
+        bool more = s.resume(lanes);
         if (more && fit_passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
           s.anomaly |= 8;
           s.rc = 9;
           more = false;
         }
-        if (more) break;
-        finish_call();  // (also a call that ended without a single trial step, e.g. residual too big at the start)
-        if (!load_next()) {
-          active = false;
-          break;
+        if (more) {
+          need = false;
+        } else {
+          finish_call();  // (also a call that ended without a single trial step, e.g. residual too big at the start)
+          if (!load_next()) {
+            active = false;
+            need = false;
+          }
         }
       }
     }

@@ -249,7 +249,9 @@ struct Nl2 {
 
   // Consume the results of the pass just made.  Returns true if another pass is wanted,
   // false when this nl2sno call is over (rc = the reference's iv(1): 3..10, 13).
-  FMC_HD bool resume();
+  // `lanes`: device only -- the mask of the lanes of this warp that make this call together (0 = the
+  // calling lane is on its own); see the comment at the definition.
+  FMC_HD bool resume(unsigned int lanes = 0u);
 
   // ------------------------------------------------------------------ pieces
   FMC_HD void init_iteration_state();
@@ -1385,202 +1387,289 @@ L430:
 }
 
 // ----------------------------------------------------------------- nl2itr, resumable
+//
+// Control flow.  The reference's nl2itr is one routine full of GO TOs (toms573.f90:772-1444); a
+// literal restatement is correct but, on a GPU, once the lanes of a warp take different branches in
+// assess they run the REST of the routine -- factorisation, Levenberg-Marquardt step, gqtstp -- in
+// separate little groups, because irreducible goto flow gives the compiler no point at which to bring
+// them back together (measured on C5, ncu source view: 18 lanes enter the routine together, 3.2
+// reach lmstep together).  The routine is therefore written as a state machine: each block between
+// two of the reference's labels is a state, a GO TO is an assignment to `st`, and the lanes of a warp
+// that are inside this call together (`lanes` = their mask) repeatedly agree on the SMALLEST pending
+// state and run exactly that one.  States are numbered along the normal flow, so lanes that took a
+// short cut wait for the others to catch up and every expensive block is entered by all the lanes
+// that need it at once.  The per-lane sequence of operations -- hence every result -- is the same as
+// in the goto form; on the host (and with lanes = 0) it is a plain sequential state machine.
+enum Nl2State {
+  ST_ENTRY = 0,   // label 20
+  ST_ASSESS = 1,  // label 300 and the dispatch on irc that follows it
+  ST_UPDATE = 2,  // label 385 ... 490: gradient, secant update
+  ST_L100 = 3,    // label 100/130: start of an iteration
+  ST_L160 = 4,    // label 160: evaluation limit
+  ST_L180 = 5,    // label 180: which step routine
+  ST_LM = 6,      // factor + lmstep
+  ST_GQ = 7,      // build_h + gqtstp
+  ST_L290 = 8,    // label 290: the new trial point
+  ST_DONE = 9
+};
+
 template <int P>
-FMC_HD bool Nl2<P>::resume() {
+FMC_HD bool Nl2<P>::resume(unsigned int lanes) {
   int l, spins = 0;
   double e, sttsst, t, t1;
+  bool more = false;
+  int st = (phase == PH_JAC) ? ST_UPDATE : ST_ENTRY;
+  (void)lanes;
 
-  if (phase == PH_JAC) goto L385;
-
-  // label 20 (toms573.f90:949-952): f = half the sum of squares; a residual norm above
-  // rlimit (or an overflowed sum) is "too big".  NaN compares false, as in the reference.
-  t = sqrt(res_f);
-  if (phase == PH_INIT) init_iteration_state();
-  if (t > k::rlimit) toobig = 1;
-  if (toobig == 0) v[F] = 0.5 * res_f;
-  if (phase == PH_TRIAL) {
-    x_is_eval = 1;
-    goto L300;
-  }
-  if (toobig != 0) {  // label 40
-    rc = 13;
-    return false;
-  }
-  adopt_jacobian();  // label 60
-
-L100:
-  if (niter >= k::mxiter) {
-    rc = 10;
-    return false;
-  }
-  {
-    int kk = niter;
-    niter = kk + 1;
-    if (kk != 0) {
-      FMC_SOLVER_LOOP
-      for (int i = 0; i < P; ++i) step[i] = d[i] * step[i];
-      v[RADIUS] = v[RADFAC] * nrm2(P, step);
+  for (;;) {
+#if defined(__CUDA_ARCH__)
+    if (lanes != 0u) {
+      const int run = __reduce_min_sync(lanes, st);
+      if (run == ST_DONE) break;
+      if (st != run) continue;
+    } else if (st == ST_DONE) {
+      break;
     }
-  }
-  // label 130
-  v[F0] = v[F];
-  kagqt = -1;
-  irc = 4;
-  hvalid = 0;
-  sused = model;
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < P; ++i) x0[i] = x[i];
-
-L160:
-  if (nfcall >= k::mxfcal) {
-    // The reference evaluates one more gradient when f < f0 (toms573.f90:1055-1061); it is
-    // only used by the covariance code, so the result x is already final.
-    if (v[F] < v[F0]) ngcall++;
-    rc = 9;
-    return false;
-  }
-
-L180:
-  if (++spins > 40) {  // safety cap: step recomputed over and over without a new evaluation
-    anomaly |= 4;
-    rc = 8;
-    return false;
-  }
-  if (model == 2) goto L220;
-  if (kalm < 0) factor();
-  if (!hvalid) {
-    FMC_SOLVER_LOOP
-    for (int i = 0; i < PP; ++i) hmat[i] = rfac[i];
-    hvalid = 1;
-  }
-  lmstep();
-  goto L290;
-L220:
-  if (!hvalid) {
-    build_h();
-    hvalid = 1;
-  }
-  gqtstp();
-
-L290:
-  if (irc == 6) goto L300;
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < P; ++i) x[i] = step[i] + x0[i];
-  nfcall = nfcall + 1;
-  toobig = 0;
-  set_fd_steps();
-  need_b = 1;
-  phase = PH_TRIAL;
-  return true;
-
-L300:
-  assess();
-#ifdef FMC_TRACE
-  if (trace && trace_len < trace_cap) {
-    double* t = trace + (size_t)trace_len * 10;
-    double piv = 0.0;
-    FMC_SOLVER_LOOP
-    for (int q = 0; q < P; ++q) piv = piv * P + (ipivot[q] - 1);
-    t[0] = irc;
-    t[1] = sused;
-    t[2] = nfcall;
-    t[3] = niter;
-    t[4] = v[F];
-    t[5] = v[RELDX];
-    t[6] = v[RADIUS];
-    t[7] = piv;
-    t[8] = restor;
-    t[9] = v[NREDUC];
-    ++trace_len;
-  }
+#else
+    if (st == ST_DONE) break;
 #endif
-  if (swtch != 0) {
-    hvalid = 0;
-    sused = sused + 2;
-    FMC_SOLVER_LOOP
-    for (int i = 0; i < 9; ++i) v[i] = vsave[i];
-  }
-  l = irc - 4;
-  stpmod = model;
-  if (l > 0) {
-    if (l == 1) goto L340;
-    if (l == 2) goto L360;
-    if (l <= 8) goto L370;
-    rc = 14;  // l == 9: bad parameters to assess (cannot occur)
-    return false;
-  }
-  // decide whether to change models (toms573.f90:1215-1235)
-  e = v[PREDUC] - v[FDIF];
-  symv(P, lky, S, step);
-  sttsst = 0.5 * dotn(P, step, lky);
-  if (model == 1) sttsst = -sttsst;
-  if (fabs(e + sttsst) * k::fuzz >= fabs(e)) goto L330;
-  model = 3 - model;
-  if (model == 1) kagqt = -1;
-  if (model == 2 && kalm > 0) kalm = 0;
-  if (-2 < l) goto L380;
-  hvalid = 0;
-  sused = sused + 2;
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < 9; ++i) vsave[i] = v[i];
-  goto L160;  // label 350 only saves r, which is not kept here
-L330:
-  if (-3 < l) goto L380;
-  v[RADIUS] = v[RADFAC] * v[DSTNRM];
-  goto L160;
-L340:
-  v[RADIUS] = v[RADFAC] * v[DSTNRM];
-  goto L160;
-L360:
-  v[RADIUS] = k::lmax0;
-  goto L180;
-L370:
-  // convergence or false convergence: x is final.  (The reference still fetches a gradient
-  // when f < f0, for the covariance matrix only: toms573.f90:1259-1262.)
-  if (v[F] < v[F0] && xirc != 14) ngcall++;
-  rc = l;
-  return false;
+    switch (st) {
+      case ST_ENTRY:
+        // label 20 (toms573.f90:949-952): f = half the sum of squares; a residual norm above
+        // rlimit (or an overflowed sum) is "too big".  NaN compares false, as in the reference.
+        t = sqrt(res_f);
+        if (phase == PH_INIT) init_iteration_state();
+        if (t > k::rlimit) toobig = 1;
+        if (toobig == 0) v[F] = 0.5 * res_f;
+        if (phase == PH_TRIAL) {
+          x_is_eval = 1;
+          st = ST_ASSESS;
+          break;
+        }
+        if (toobig != 0) {  // label 40
+          rc = 13;
+          st = ST_DONE;
+          break;
+        }
+        adopt_jacobian();  // label 60
+        st = ST_L100;
+        break;
 
-L380:
-  if (!x_is_eval) {
-    // assess went back to an earlier trial point of this iteration: its Jacobian and
-    // J(x0)^T r(x) need a pass of their own.
-    set_fd_steps();
-    need_b = 1;
-    phase = PH_JAC;
-    return true;
-  }
-L385:
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < P; ++i) lky[i] = res_lky[i];  // lky = J(x0)^T r(x), toms573.f90:1268-1293
-  if (irc == 3) hess_times_step();                  // label 410
-  ngcall = ngcall + 1;                              // label 450
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < P; ++i) w[i] = g[i];          // g0
-  adopt_jacobian();                                 // labels 50-60 at the new x
-  // label 460
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < P; ++i) w[i] = -w[i] + g[i];  // g - g0
-  if (irc == 3) {
-    FMC_SOLVER_LOOP
-    for (int i = 0; i < P; ++i) tmp1[i] = (tmp1[i] - w[i]) / d[i];
-    if (nrm2(P, tmp1) <= v[DGNORM] * k::tuner4) {
-      v[RADFAC] = k::incfac;
-    } else if (dotn(P, g, step) >= v[GTSTEP] * k::tuner5) {
-    } else {
-      v[RADFAC] = k::incfac;
+      case ST_L100:
+        if (niter >= k::mxiter) {
+          rc = 10;
+          st = ST_DONE;
+          break;
+        }
+        {
+          int kk = niter;
+          niter = kk + 1;
+          if (kk != 0) {
+            FMC_SOLVER_LOOP
+            for (int i = 0; i < P; ++i) step[i] = d[i] * step[i];
+            v[RADIUS] = v[RADFAC] * nrm2(P, step);
+          }
+        }
+        // label 130
+        v[F0] = v[F];
+        kagqt = -1;
+        irc = 4;
+        hvalid = 0;
+        sused = model;
+        FMC_SOLVER_LOOP
+        for (int i = 0; i < P; ++i) x0[i] = x[i];
+        st = ST_L160;
+        break;
+
+      case ST_L160:
+        if (nfcall >= k::mxfcal) {
+          // The reference evaluates one more gradient when f < f0 (toms573.f90:1055-1061); it is
+          // only used by the covariance code, so the result x is already final.
+          if (v[F] < v[F0]) ngcall++;
+          rc = 9;
+          st = ST_DONE;
+          break;
+        }
+        st = ST_L180;
+        break;
+
+      case ST_L180:
+        if (++spins > 40) {  // safety cap: step recomputed over and over without a new evaluation
+          anomaly |= 4;
+          rc = 8;
+          st = ST_DONE;
+          break;
+        }
+        st = (model == 2) ? ST_GQ : ST_LM;
+        break;
+
+      case ST_LM:
+        if (kalm < 0) factor();
+        if (!hvalid) {
+          FMC_SOLVER_LOOP
+          for (int i = 0; i < PP; ++i) hmat[i] = rfac[i];
+          hvalid = 1;
+        }
+        lmstep();
+        st = ST_L290;
+        break;
+
+      case ST_GQ:  // label 220
+        if (!hvalid) {
+          build_h();
+          hvalid = 1;
+        }
+        gqtstp();
+        st = ST_L290;
+        break;
+
+      case ST_L290:
+        if (irc == 6) {
+          st = ST_ASSESS;
+          break;
+        }
+        FMC_SOLVER_LOOP
+        for (int i = 0; i < P; ++i) x[i] = step[i] + x0[i];
+        nfcall = nfcall + 1;
+        toobig = 0;
+        set_fd_steps();
+        need_b = 1;
+        phase = PH_TRIAL;
+        more = true;
+        st = ST_DONE;
+        break;
+
+      case ST_ASSESS:  // label 300
+        assess();
+#ifdef FMC_TRACE
+        if (trace && trace_len < trace_cap) {
+          double* tr = trace + (size_t)trace_len * 10;
+          double piv = 0.0;
+          FMC_SOLVER_LOOP
+          for (int q = 0; q < P; ++q) piv = piv * P + (ipivot[q] - 1);
+          tr[0] = irc;
+          tr[1] = sused;
+          tr[2] = nfcall;
+          tr[3] = niter;
+          tr[4] = v[F];
+          tr[5] = v[RELDX];
+          tr[6] = v[RADIUS];
+          tr[7] = piv;
+          tr[8] = restor;
+          tr[9] = v[NREDUC];
+          ++trace_len;
+        }
+#endif
+        if (swtch != 0) {
+          hvalid = 0;
+          sused = sused + 2;
+          FMC_SOLVER_LOOP
+          for (int i = 0; i < 9; ++i) v[i] = vsave[i];
+        }
+        l = irc - 4;
+        stpmod = model;
+        if (l > 0) {
+          if (l == 1) {  // label 340
+            v[RADIUS] = v[RADFAC] * v[DSTNRM];
+            st = ST_L160;
+            break;
+          }
+          if (l == 2) {  // label 360
+            v[RADIUS] = k::lmax0;
+            st = ST_L180;
+            break;
+          }
+          if (l <= 8) {  // label 370
+            // convergence or false convergence: x is final.  (The reference still fetches a gradient
+            // when f < f0, for the covariance matrix only: toms573.f90:1259-1262.)
+            if (v[F] < v[F0] && xirc != 14) ngcall++;
+            rc = l;
+            st = ST_DONE;
+            break;
+          }
+          rc = 14;  // l == 9: bad parameters to assess (cannot occur)
+          st = ST_DONE;
+          break;
+        }
+        {
+          // decide whether to change models (toms573.f90:1215-1235)
+          e = v[PREDUC] - v[FDIF];
+          symv(P, lky, S, step);
+          sttsst = 0.5 * dotn(P, step, lky);
+          if (model == 1) sttsst = -sttsst;
+          if (fabs(e + sttsst) * k::fuzz >= fabs(e)) {  // label 330
+            if (!(-3 < l)) {
+              v[RADIUS] = v[RADFAC] * v[DSTNRM];
+              st = ST_L160;
+              break;
+            }
+          } else {
+            model = 3 - model;
+            if (model == 1) kagqt = -1;
+            if (model == 2 && kalm > 0) kalm = 0;
+            if (!(-2 < l)) {
+              hvalid = 0;
+              sused = sused + 2;
+              FMC_SOLVER_LOOP
+              for (int i = 0; i < 9; ++i) vsave[i] = v[i];
+              st = ST_L160;  // label 350 only saves r, which is not kept here
+              break;
+            }
+          }
+        }
+        // label 380
+        if (!x_is_eval) {
+          // assess went back to an earlier trial point of this iteration: its Jacobian and
+          // J(x0)^T r(x) need a pass of their own.
+          set_fd_steps();
+          need_b = 1;
+          phase = PH_JAC;
+          more = true;
+          st = ST_DONE;
+          break;
+        }
+        st = ST_UPDATE;
+        break;
+
+      case ST_UPDATE:  // label 385
+        FMC_SOLVER_LOOP
+        for (int i = 0; i < P; ++i) lky[i] = res_lky[i];  // lky = J(x0)^T r(x), toms573.f90:1268-1293
+        if (irc == 3) hess_times_step();                  // label 410
+        ngcall = ngcall + 1;                              // label 450
+        FMC_SOLVER_LOOP
+        for (int i = 0; i < P; ++i) w[i] = g[i];          // g0
+        adopt_jacobian();                                 // labels 50-60 at the new x
+        // label 460
+        FMC_SOLVER_LOOP
+        for (int i = 0; i < P; ++i) w[i] = -w[i] + g[i];  // g - g0
+        if (irc == 3) {
+          FMC_SOLVER_LOOP
+          for (int i = 0; i < P; ++i) tmp1[i] = (tmp1[i] - w[i]) / d[i];
+          if (nrm2(P, tmp1) <= v[DGNORM] * k::tuner4) {
+            v[RADFAC] = k::incfac;
+          } else if (dotn(P, g, step) >= v[GTSTEP] * k::tuner5) {
+          } else {
+            v[RADFAC] = k::incfac;
+          }
+        }
+        // label 490: y = (J(x) - J(x0))^T r(x), sizing factor, secant update of S
+        FMC_SOLVER_LOOP
+        for (int i = 0; i < P; ++i) lky[i] = -lky[i] + g[i];
+        symv(P, tmp1, S, step);
+        t1 = fabs(dotn(P, step, tmp1));
+        t = fabs(dotn(P, step, lky));
+        size_ = 1.0;
+        if (t < t1) size_ = t / t1;
+        slupdt(w);
+        st = ST_L100;
+        break;
+
+      default:
+        st = ST_DONE;
+        break;
     }
   }
-  // label 490: y = (J(x) - J(x0))^T r(x), sizing factor, secant update of S
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < P; ++i) lky[i] = -lky[i] + g[i];
-  symv(P, tmp1, S, step);
-  t1 = fabs(dotn(P, step, tmp1));
-  t = fabs(dotn(P, step, lky));
-  size_ = 1.0;
-  if (t < t1) size_ = t / t1;
-  slupdt(w);
-  goto L100;
+  return more;
 }
 
 }  // namespace fmc

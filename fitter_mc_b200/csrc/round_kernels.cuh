@@ -89,10 +89,12 @@ __global__ void __launch_bounds__(FMC_ROUND_SOLVE_THREADS) round_solve_kernel(co
   constexpr int W = (int)((sizeof(Nl2<P>) + 7) / 8);  // state_words<P>()
   const long long C = ra.nslots;
   const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= C) return;
   const unsigned int round = ra.ctl[RC_ROUND];
-  long long fit = round == 0 ? -1 : ra.slot_fit[slot];  // round 0 of a chunk: every slot takes a fit
-  if (round != 0 && fit < 0) return;                    // idle slot (the chunk is draining)
+  // No lane leaves before the end: the lanes of a warp vote on who calls the solver step together.
+  // round 0 of a chunk: every slot takes a fit; later rounds: only slots whose fit has just had a pass.
+  long long fit = (slot < C && round != 0) ? ra.slot_fit[slot] : -1;
+  enum { IDLE = 0, FETCH = 1, STEP = 2, PARK = 3 };
+  int todo = slot >= C ? IDLE : (round == 0 ? FETCH : (fit >= 0 ? STEP : IDLE));
 
   const long long cap = ap->cap, nres = ap->nres;
   union Image {
@@ -102,74 +104,82 @@ __global__ void __launch_bounds__(FMC_ROUND_SOLVE_THREADS) round_solve_kernel(co
   } im;
   Nl2<P>& s = im.s;
   int call = 0, fit_passes = 0;
-  bool have = false;
-  if (fit >= 0) {
+  if (todo == STEP) {
 #pragma unroll 4
     for (int w = 0; w < W; ++w) im.w[w] = ra.state[(long long)w * C + slot];
     call = ra.slot_meta[slot];
     fit_passes = ra.slot_meta[C + slot] + 1;  // the pass whose sums are in the image
-    have = true;
   }
   for (;;) {
-    if (have) {
-      bool more = s.resume();
+    if (todo == FETCH) {
+      // ---- take the next fit of the chunk: starting point + the sums of its initial pass (stage A)
+      const unsigned long long kk = atomicAdd(ap->next_id, 1ULL);
+      if (kk >= (unsigned long long)nres) {
+        ra.slot_fit[slot] = -1;
+        todo = IDLE;
+      } else {
+        fit = (long long)kk;
+        double xs[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) xs[i] = ap->start[i];
+        s.reset_fit();
+        s.begin(xs);
+        s.res_f = ap->init[fit];
+#pragma unroll
+        for (int i = 0; i < P; ++i) s.res_g[i] = ap->init[(size_t)(1 + i) * cap + fit];
+#pragma unroll
+        for (int i = 0; i < PP; ++i) s.res_G[i] = ap->init[(size_t)(1 + P + i) * cap + fit];
+        call = 0;
+        fit_passes = 1;
+        todo = STEP;
+      }
+    }
+    const unsigned int lanes = __ballot_sync(0xffffffffu, todo == STEP);
+    if (lanes == 0u) break;
+    if (todo == STEP) {
+      bool more = s.resume(lanes);
       if (more && fit_passes > 2 * (k::mxfcal + k::mxiter)) {  // safety cap on passes per call
         s.anomaly |= 8;
         s.rc = 9;
         more = false;
       }
-      if (more) break;
-      // ---- end of an nl2sno call
-      if (s.anomaly != 0 && ap->anom != nullptr) {
-        const unsigned long long kk = atomicAdd(ap->anom, 1ULL);
-        if (kk < (unsigned long long)ANOM_CAP) {
-          ap->anom[1 + 2 * kk] = (unsigned long long)(ap->first + fit);
-          ap->anom[2 + 2 * kk] = (unsigned long long)(s.anomaly | (call << 8));
+      if (more) {
+        todo = PARK;
+      } else {
+        // ---- end of an nl2sno call
+        if (s.anomaly != 0 && ap->anom != nullptr) {
+          const unsigned long long kk = atomicAdd(ap->anom, 1ULL);
+          if (kk < (unsigned long long)ANOM_CAP) {
+            ap->anom[1 + 2 * kk] = (unsigned long long)(ap->first + fit);
+            ap->anom[2 + 2 * kk] = (unsigned long long)(s.anomaly | (call << 8));
+          }
+          s.anomaly = 0;
         }
-        s.anomaly = 0;
+        int* cnt = ap->cnt + (size_t)(5 * call) * cap + fit;
+        cnt[0 * cap] = s.rc;
+        cnt[1 * cap] = s.nfcall;
+        cnt[2 * cap] = s.ngcall;
+        cnt[3 * cap] = s.niter;
+        cnt[4 * cap] = fit_passes;
+        if (call == 0) {
+          // fit_data calls nl2sno a second time from the answer of the first (bootstrap.f90:222-225):
+          // the fit stays in its slot; iv(mlstgd) and lsvmin's generator carry over as in the reference
+          double xs[P];
+#pragma unroll
+          for (int i = 0; i < P; ++i) xs[i] = s.x[i];
+          s.begin(xs);
+          call = 1;
+          fit_passes = 0;
+          todo = PARK;  // wants the first evaluation of the call: residual + Jacobian at x, D = 1, no x0 part
+        } else {
+#pragma unroll
+          for (int i = 0; i < P; ++i) ap->xbuf[(size_t)i * cap + fit] = s.x[i];
+          todo = FETCH;
+        }
       }
-      int* cnt = ap->cnt + (size_t)(5 * call) * cap + fit;
-      cnt[0 * cap] = s.rc;
-      cnt[1 * cap] = s.nfcall;
-      cnt[2 * cap] = s.ngcall;
-      cnt[3 * cap] = s.niter;
-      cnt[4 * cap] = fit_passes;
-      if (call == 0) {
-        // fit_data calls nl2sno a second time from the answer of the first (bootstrap.f90:222-225):
-        // the fit stays in its slot; iv(mlstgd) and lsvmin's generator carry over as in the reference
-        double xs[P];
-#pragma unroll
-        for (int i = 0; i < P; ++i) xs[i] = s.x[i];
-        s.begin(xs);
-        call = 1;
-        fit_passes = 0;
-        break;  // wants the first evaluation of the call: residual + Jacobian at x, D = 1, no x0 part
-      }
-#pragma unroll
-      for (int i = 0; i < P; ++i) ap->xbuf[(size_t)i * cap + fit] = s.x[i];
-      have = false;
     }
-    // ---- take the next fit of the chunk: starting point + the sums of its initial pass (stage A)
-    const unsigned long long kk = atomicAdd(ap->next_id, 1ULL);
-    if (kk >= (unsigned long long)nres) {
-      ra.slot_fit[slot] = -1;
-      return;
-    }
-    fit = (long long)kk;
-    double xs[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) xs[i] = ap->start[i];
-    s.reset_fit();
-    s.begin(xs);
-    s.res_f = ap->init[fit];
-#pragma unroll
-    for (int i = 0; i < P; ++i) s.res_g[i] = ap->init[(size_t)(1 + i) * cap + fit];
-#pragma unroll
-    for (int i = 0; i < PP; ++i) s.res_G[i] = ap->init[(size_t)(1 + P + i) * cap + fit];
-    call = 0;
-    fit_passes = 1;
-    have = true;
   }
+  if (todo != PARK) return;
   // ---- another pass is wanted: park the state, queue the slot
 #pragma unroll 4
   for (int w = 0; w < W; ++w) ra.state[(long long)w * C + slot] = im.w[w];
