@@ -30,7 +30,8 @@ class FmcError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libfmc_b200.so")
+    """The CUDA library: libfmc_b200.so next to this file, or the build named by FMC_B200_LIB."""
+    return os.environ.get("FMC_B200_LIB") or os.path.join(_HERE, "libfmc_b200.so")
 
 
 _lib = None
@@ -404,11 +405,11 @@ class Context:
         """"refill" (one persistent kernel per nl2sno call, threads take the next fit from a counter) or
         "rounds" (solver steps and passes in separate kernels alternating inside a CUDA graph WHILE node,
         fits compacted between rounds -- csrc/round_kernels.cuh).  Same per-fit arithmetic."""
-        code = {"refill": 0, 0: 0, "rounds": 1, 1: 1}[schedule]
+        code = {"refill": 0, 0: 0, "rounds": 1, 1: 1, "auto": 2, 2: 2}[schedule]
         _check(lib().fmc_set_schedule(self._h, code), "fmc_set_schedule")
 
     def schedule(self):
-        return {0: "refill", 1: "rounds"}[lib().fmc_get_schedule(self._h)]
+        return {0: "refill", 1: "rounds", 2: "auto"}[lib().fmc_get_schedule(self._h)]
 
     def set_histogram(self, nbins, lo=None, hi=None):
         """Bin every fitted parameter and property on the device (replaces histogram_<prop>.dat,

@@ -268,7 +268,8 @@ struct fmc_context {
   int comm_nranks = 1;
   int jac = fmc::JAC_FD;  // how Jacobian rows are formed (fmc_set_jacobian_mode)
   int mapping = 0;        // 0 = one fit per thread, 1 = one fit per warp (fmc_set_fit_mapping)
-  int schedule = 0;       // FMC_SCHEDULE_REFILL or FMC_SCHEDULE_ROUNDS (fmc_set_schedule)
+  int schedule = FMC_SCHEDULE_AUTO;  // FMC_SCHEDULE_REFILL, _ROUNDS or _AUTO (fmc_set_schedule)
+  int schedule_used = FMC_SCHEDULE_REFILL;  // what the last launch resolved AUTO to
   // ---- round schedule (round_kernels.cuh): slot pool, lists, control words, the WHILE graph
   fmc::RoundArgs rs{0, nullptr, nullptr, nullptr, nullptr, nullptr};
   long long rs_state_cap = 0;            // 64-bit words allocated for rs.state
@@ -301,8 +302,9 @@ struct fmc_context {
 static int default_schedule() {
   static const int v = [] {
     const char* e = std::getenv("FMC_SCHEDULE");
-    return (e && (e[0] == 'r' || e[0] == 'R') && (e[1] == 'o' || e[1] == 'O')) ? FMC_SCHEDULE_ROUNDS
-                                                                                : FMC_SCHEDULE_REFILL;
+    if (e && (e[0] == 'r' || e[0] == 'R') && (e[1] == 'o' || e[1] == 'O')) return FMC_SCHEDULE_ROUNDS;
+    if (e && (e[0] == 'r' || e[0] == 'R') && (e[1] == 'e' || e[1] == 'E')) return FMC_SCHEDULE_REFILL;
+    return FMC_SCHEDULE_AUTO;
   }();
   return v;
 }
@@ -462,6 +464,7 @@ const char* fmc_strerror(int code) {
     case FMC_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case FMC_ERR_CUDA: return "a CUDA call failed (see fmc_last_cuda_error)";
     case FMC_ERR_BAD_MODEL: return "model id out of range";
+    case FMC_ERR_UNSUPPORTED: return "not part of this build of the library";
     case FMC_ERR_BAD_ARG: return "invalid argument";
     case FMC_ERR_NO_DATA: return "fmc_set_data has not been called";
     case FMC_ERR_STATE: return "no launch in flight";
@@ -684,6 +687,11 @@ int fmc_set_jacobian_mode(fmc_context* c, int mode) {
 
 int fmc_set_fit_mapping(fmc_context* c, int mapping) {
   if (mapping != FMC_FIT_PER_THREAD && mapping != FMC_FIT_PER_WARP) return FMC_ERR_BAD_ARG;
+#ifndef FMC_WITH_WARP_MAPPING
+  // The warp-per-fit kernels lost the measurement on every configuration (profiles/r2_mapping_*.json:
+  // 0.47-0.70 of the thread-per-fit rate on C4, 0.47 on C5) and are not part of the default build.
+  if (mapping == FMC_FIT_PER_WARP) return FMC_ERR_UNSUPPORTED;
+#endif
   if (c)
     c->mapping = mapping;
   else
@@ -692,7 +700,8 @@ int fmc_set_fit_mapping(fmc_context* c, int mapping) {
 }
 
 int fmc_set_schedule(fmc_context* c, int schedule) {
-  if (schedule != FMC_SCHEDULE_REFILL && schedule != FMC_SCHEDULE_ROUNDS) return FMC_ERR_BAD_ARG;
+  if (schedule != FMC_SCHEDULE_REFILL && schedule != FMC_SCHEDULE_ROUNDS && schedule != FMC_SCHEDULE_AUTO)
+    return FMC_ERR_BAD_ARG;
   if (c)
     c->schedule = schedule;
   else
@@ -700,7 +709,10 @@ int fmc_set_schedule(fmc_context* c, int schedule) {
   return FMC_OK;
 }
 
-int fmc_get_schedule(const fmc_context* c) { return c ? c->schedule : g_default_schedule; }
+int fmc_get_schedule(const fmc_context* c) {
+  if (!c) return g_default_schedule >= 0 ? g_default_schedule : default_schedule();
+  return c->schedule == FMC_SCHEDULE_AUTO ? c->schedule_used : c->schedule;  // AUTO: what the last launch chose
+}
 
 int fmc_model_has_analytic_jacobian(int model) {
   if (model < 0 || model >= fmc_model_count()) return 0;
@@ -916,11 +928,24 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   const int jac = c->jac;
   if (jac == fmc::JAC_ANALYTIC && !m.analytic) return FMC_ERR_BAD_ARG;  // double-only model_y, no model_grad
   const bool per_warp = c->mapping == FMC_FIT_PER_WARP;
-  const bool rounds = !per_warp && c->schedule == FMC_SCHEDULE_ROUNDS;
+  // FMC_SCHEDULE_AUTO, by measurement (profiles/r2_schedule_*.json): the round schedule wins where the pass
+  // kernel gains from shedding the solver's state -- rows that do not fit in shared memory, or so many
+  // parameters that the row loop needs every register (C4: n = 10^4, p = 10, +19 %) -- and loses on
+  // small, well-behaved fits (C1, C2: the solve kernel's trip through HBM costs more than the divergence
+  // it removes).  Strongly diverging fits (C5) also gain (+19 %), but that is not knowable beforehand:
+  // set FMC_SCHEDULE_ROUNDS for them.
+  const int schedule = c->schedule == FMC_SCHEDULE_AUTO ? ((!smem || P > 6) ? FMC_SCHEDULE_ROUNDS : FMC_SCHEDULE_REFILL)
+                                                        : c->schedule;
+  c->schedule_used = schedule;
+  const bool rounds = !per_warp && schedule == FMC_SCHEDULE_ROUNDS;
   const fmc::RoundEntry rentry = rounds ? fmc::fmc_round_entry(c->model) : fmc::RoundEntry{0, nullptr, nullptr, nullptr};
   if (rounds && !rentry.enqueue_round) return FMC_ERR_BAD_MODEL;
   c->rs_used = false;
+#ifdef FMC_WITH_WARP_MAPPING
   const fmc::WarpEntry wentry = per_warp ? fmc::fmc_warp_entry(c->model) : fmc::WarpEntry{nullptr, nullptr, 0};
+#else
+  const fmc::WarpEntry wentry = fmc::WarpEntry{nullptr, nullptr, 0};  // (fmc_set_fit_mapping refuses FMC_FIT_PER_WARP)
+#endif
   fmc::WarpArgs wa;
   std::memset(&wa, 0, sizeof(wa));
   if (per_warp) {

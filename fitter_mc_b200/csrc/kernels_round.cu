@@ -1,6 +1,10 @@
 // Round-schedule kernels (round_kernels.cuh) of the compiled-in models.  Compiled once per model
 // (-DFMC_ROUND_MODEL=k, see the Makefile) so that the instantiations build in parallel and the
 // refill kernels are compiled exactly as before.
+// The solver is compiled with rolled loops and out-of-line helpers here (nl2_solver.cuh, FMC_SOLVER_ROLLED):
+// the solve kernel keeps its state in shared (or local) memory where dynamic indexing costs nothing, and
+// what it is short of is instruction cache.  No other kernel of this translation unit contains solver code.
+#define FMC_SOLVER_ROLLED 1
 #include "models/model_user.cuh"
 #include "models/models_bench.cuh"
 #include "round_kernels.cuh"

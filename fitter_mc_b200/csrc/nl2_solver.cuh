@@ -36,10 +36,19 @@
 // instructions (400 KB) of branchy code against a 32 KB instruction cache -- measured (ncu,
 // profiles/r2_ncu_c4_warp_unrolled_summary.txt) as 4.3 "no instruction" stall cycles per issued
 // instruction, the solver step costing more than the pass over 10^4 data points it follows.
+//
+// The round schedule's solve kernel (round_kernels.cuh) defines it as well: there the state sits in
+// shared memory too, and what limits the kernel is the SIZE of the code its divergent lanes walk
+// through (ncu: 16 "no instruction" stall cycles per issued instruction with the unrolled, fully inlined
+// 20 000-instruction solver).  In that mode the small dense helpers -- inlined at some fifty call sites,
+// each with its copy of the FP64 square root and of v2norm's overflow-safe fallback -- become real
+// functions (FMC_SOLVER_FN).
 #if defined(FMC_SOLVER_ROLLED) && defined(__CUDACC__)
 #define FMC_SOLVER_LOOP _Pragma("unroll 1")
+#define FMC_SOLVER_FN inline __noinline__
 #else
 #define FMC_SOLVER_LOOP
+#define FMC_SOLVER_FN inline
 #endif
 
 namespace fmc {
@@ -80,7 +89,11 @@ FMC_HD inline double nrm2_scaled(int n, const double* x) {
   }
   return scale * sqrt(t);
 }
+#if defined(FMC_SOLVER_ROLLED) && defined(__CUDACC__)
+FMC_HD FMC_SOLVER_FN double nrm2(int n, const double* x) {
+#else
 FMC_HD FMC_INLINE double nrm2(int n, const double* x) {
+#endif
   double s = 0.0;
   FMC_SOLVER_LOOP
   for (int i = 0; i < n; ++i) s = fma(x[i], x[i], s);
@@ -89,7 +102,7 @@ FMC_HD FMC_INLINE double nrm2(int n, const double* x) {
 }
 
 // Solve (L**T) x = y, L packed lower-by-rows (litvmu, toms573.f90:3334).
-FMC_HD inline void ltsolve_t(int n, double* x, const double* l, const double* y) {
+FMC_HD FMC_SOLVER_FN void ltsolve_t(int n, double* x, const double* l, const double* y) {
   FMC_SOLVER_LOOP
   for (int i = 0; i < n; ++i) x[i] = y[i];
   int i0 = n * (n + 1) / 2;
@@ -106,7 +119,7 @@ FMC_HD inline void ltsolve_t(int n, double* x, const double* l, const double* y)
 }
 
 // Solve L x = y (livmul, toms573.f90:3367).
-FMC_HD inline void ltsolve(int n, double* x, const double* l, const double* y) {
+FMC_HD FMC_SOLVER_FN void ltsolve(int n, double* x, const double* l, const double* y) {
   int kk = 1;
   FMC_SOLVER_LOOP
   for (; kk <= n; ++kk) {
@@ -126,7 +139,7 @@ FMC_HD inline void ltsolve(int n, double* x, const double* l, const double* y) {
 
 // Cholesky factor by rows, packed (lsqrt, toms573.f90:3842).  Returns 0 or the index of
 // the first non-positive reduced diagonal (stored in place of the diagonal).
-FMC_HD inline int chol_rows(int n, double* l, const double* a) {
+FMC_HD FMC_SOLVER_FN int chol_rows(int n, double* l, const double* a) {
   int i0 = 0;
   FMC_SOLVER_LOOP
   for (int i = 1; i <= n; ++i) {
@@ -154,7 +167,7 @@ FMC_HD inline int chol_rows(int n, double* l, const double* a) {
 }
 
 // y = S x for packed lower-by-rows symmetric S (slvmul, toms573.f90:4697).
-FMC_HD inline void symv(int p, double* y, const double* s, const double* x) {
+FMC_HD FMC_SOLVER_FN void symv(int p, double* y, const double* s, const double* x) {
   int j = 0;
   FMC_SOLVER_LOOP
   for (int i = 1; i <= p; ++i) {

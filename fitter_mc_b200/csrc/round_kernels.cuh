@@ -81,32 +81,100 @@ struct StateLayout {
 };
 
 // ---------------------------------------------------------------------------------------
+// Where the solver state of a slot lives while its step runs, and how many slots share a warp.
+//
+// The state (Nl2<P>: 1.5 KB for p = 4) is indexed dynamically all over the solver, so in a thread's
+// own frame it is LOCAL memory: with 640 resident threads per SM that is 1 MB per SM against a 256 KB
+// L1, every access of the divergent solver code an L2 round trip (ncu, C5: 16 long-scoreboard stall
+// cycles per issued instruction, 2.2 GB of DRAM traffic per launch for 0.34 GB of state).  For small p
+// the images are therefore staged in SHARED memory -- image j of a block at word j * STRIDE, STRIDE
+// odd, so that lanes touching the same member (or different members) never share a bank -- filled by
+// 8-byte cp.async straight from the word-major pool (all 32 lanes of a warp copy, coalesced, no
+// registers in between) and written back the same way.
+//
+// Shared memory then bounds the slots in flight per SM (128 for p = 4: four warps), and the solver
+// step is latency-bound, branchy code: ncu on C5 shows 4 of 32 lanes active per issued instruction.
+// That is NOT 32 lanes each walking its own path -- giving a warp only LANES = 16 / 8 / 4 slots (its
+// other lanes help with the copies and idle through the step; 2x / 4x / 8x the warps for the same
+// shared memory) was measured SLOWER on C5 and C2 (5.66 / 5.24 / 4.57 against 5.80e5 fits/s on C5,
+// profiles/r2_solve_lanes.json): a warp's instruction stream is set by its slowest lane (the number of
+// More-Hebden iterations in lmstep), not by the sum over its lanes, so more, emptier warps execute
+// more instructions in total and thrash the instruction cache again.  LANES stays 32.
+// Large p (image > SMEM_STATE_MAX_WORDS) keeps the local frame: there the pass over 10^4 rows dwarfs
+// the solver step anyway.
+constexpr int SMEM_STATE_MAX_WORDS = 224;
+#ifndef FMC_ROUND_SOLVE_LANES
+#define FMC_ROUND_SOLVE_LANES 32
+#endif
+template <int P>
+struct SolveCfg {
+  static constexpr int W = (int)((sizeof(Nl2<P>) + 7) / 8);       // = state_words<P>()
+  static constexpr bool IN_SMEM = W <= SMEM_STATE_MAX_WORDS;
+  static constexpr int LANES = IN_SMEM ? FMC_ROUND_SOLVE_LANES : 32;   // slots per warp
+  // one-warp blocks when a warp's images fill a quarter of the SM's shared memory: a block then ends with its warp
+  static constexpr int THREADS = (IN_SMEM && LANES == 32) ? 32 : FMC_ROUND_SOLVE_THREADS;
+  static constexpr int SLOTS = THREADS / 32 * LANES;                // slots per block
+  static constexpr int STRIDE = W | 1;                              // words between neighbouring images (odd)
+  static constexpr size_t SMEM_BYTES = IN_SMEM ? sizeof(unsigned long long) * SLOTS * STRIDE : 0;
+};
+
+FMC_INLINE __device__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+FMC_INLINE __device__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 template <class M, int JAC>
-__global__ void __launch_bounds__(FMC_ROUND_SOLVE_THREADS) round_solve_kernel(const KernelArgs* __restrict__ ap,
-                                                                              const RoundArgs ra) {
+__global__ void __launch_bounds__(SolveCfg<M::NPARAM>::THREADS) round_solve_kernel(const KernelArgs* __restrict__ ap,
+                                                                                   const RoundArgs ra) {
   constexpr int P = M::NPARAM;
   constexpr int PP = P * (P + 1) / 2;
-  constexpr int W = (int)((sizeof(Nl2<P>) + 7) / 8);  // state_words<P>()
+  using Cfg = SolveCfg<P>;
+  constexpr int W = Cfg::W;
+  constexpr bool IN_SMEM = Cfg::IN_SMEM;
   const long long C = ra.nslots;
-  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // slots of this warp: [wslot0, wslot0 + LANES), one per lane < LANES
+  const long long wslot0 = ((long long)blockIdx.x * (Cfg::THREADS / 32) + warp) * Cfg::LANES;
+  const long long slot = lane < Cfg::LANES ? wslot0 + lane : C;
   const unsigned int round = ra.ctl[RC_ROUND];
   // No lane leaves before the end: the lanes of a warp vote on who calls the solver step together.
   // round 0 of a chunk: every slot takes a fit; later rounds: only slots whose fit has just had a pass.
   long long fit = (slot < C && round != 0) ? ra.slot_fit[slot] : -1;
   enum { IDLE = 0, FETCH = 1, STEP = 2, PARK = 3 };
   int todo = slot >= C ? IDLE : (round == 0 ? FETCH : (fit >= 0 ? STEP : IDLE));
+  if (IN_SMEM && !__any_sync(0xffffffffu, todo != IDLE)) return;  // (a warp of idle slots: nothing to stage)
 
   const long long cap = ap->cap, nres = ap->nres;
+  extern __shared__ __align__(16) unsigned long long solve_smem[];
   union Image {
     Nl2<P> s;
     unsigned long long w[W];
     __device__ Image() {}
-  } im;
-  Nl2<P>& s = im.s;
+  };
+  Image local_image;  // (unused, and removed by the compiler, when the images are in shared memory)
+  unsigned long long* const wimg = solve_smem + (size_t)warp * Cfg::LANES * Cfg::STRIDE;  // the warp's images
+  unsigned long long* const img = IN_SMEM ? wimg + (size_t)(lane < Cfg::LANES ? lane : 0) * Cfg::STRIDE : local_image.w;
+  Nl2<P>& s = *reinterpret_cast<Nl2<P>*>(img);
   int call = 0, fit_passes = 0;
-  if (todo == STEP) {
+  if constexpr (IN_SMEM) {
+    // all 32 lanes copy the warp's LANES images: element e = (word w, image j), j fastest -- consecutive
+    // lanes read consecutive slots of one word (the pool is word-major)
+    if (round != 0) {
+      const int nvalid = (int)((C - wslot0 < (long long)Cfg::LANES) ? (C - wslot0) : (long long)Cfg::LANES);
+      for (int e = lane; e < W * Cfg::LANES; e += 32) {
+        const int w = e / Cfg::LANES, j = e % Cfg::LANES;
+        if (j < nvalid) cp_async_8(wimg + (size_t)j * Cfg::STRIDE + w, ra.state + (long long)w * C + wslot0 + j);
+      }
+      cp_async_wait_all();
+    }
+    __syncwarp();
+  } else if (todo == STEP) {
 #pragma unroll 4
-    for (int w = 0; w < W; ++w) im.w[w] = ra.state[(long long)w * C + slot];
+    for (int w = 0; w < W; ++w) img[w] = ra.state[(long long)w * C + slot];
+  }
+  if (todo == STEP) {
     call = ra.slot_meta[slot];
     fit_passes = ra.slot_meta[C + slot] + 1;  // the pass whose sums are in the image
   }
@@ -125,9 +193,9 @@ __global__ void __launch_bounds__(FMC_ROUND_SOLVE_THREADS) round_solve_kernel(co
         s.reset_fit();
         s.begin(xs);
         s.res_f = ap->init[fit];
-#pragma unroll
+        FMC_SOLVER_LOOP
         for (int i = 0; i < P; ++i) s.res_g[i] = ap->init[(size_t)(1 + i) * cap + fit];
-#pragma unroll
+        FMC_SOLVER_LOOP
         for (int i = 0; i < PP; ++i) s.res_G[i] = ap->init[(size_t)(1 + P + i) * cap + fit];
         call = 0;
         fit_passes = 1;
@@ -179,10 +247,20 @@ __global__ void __launch_bounds__(FMC_ROUND_SOLVE_THREADS) round_solve_kernel(co
       }
     }
   }
-  if (todo != PARK) return;
-  // ---- another pass is wanted: park the state, queue the slot
-#pragma unroll 4
-  for (int w = 0; w < W; ++w) ra.state[(long long)w * C + slot] = im.w[w];
+  // ---- slots that want another pass: park the state, queue the slot
+  if constexpr (IN_SMEM) {
+    __syncwarp();
+    const unsigned int parked = __ballot_sync(0xffffffffu, todo == PARK);
+    for (int e = lane; e < W * Cfg::LANES; e += 32) {
+      const int w = e / Cfg::LANES, j = e % Cfg::LANES;
+      if ((parked >> j) & 1u) ra.state[(long long)w * C + wslot0 + j] = wimg[(size_t)j * Cfg::STRIDE + w];
+    }
+    if (todo != PARK) return;
+  } else {
+    if (todo != PARK) return;
+#pragma unroll 8
+    for (int w = 0; w < W; ++w) ra.state[(long long)w * C + slot] = img[w];
+  }
   ra.slot_fit[slot] = fit;
   ra.slot_meta[slot] = call;
   ra.slot_meta[C + slot] = fit_passes;
@@ -386,11 +464,12 @@ struct RoundBinding {
   static cudaError_t enqueue_round(const KernelArgs* ap, const RoundArgs& ra, bool inject, bool smem, int jac,
                                    size_t shmem, cudaGraphConditionalHandle handle, int use_handle,
                                    cudaStream_t st) {
-    const unsigned int sgrid = (unsigned int)((ra.nslots + FMC_ROUND_SOLVE_THREADS - 1) / FMC_ROUND_SOLVE_THREADS);
+    constexpr int ST = SolveCfg<M::NPARAM>::THREADS, SS = SolveCfg<M::NPARAM>::SLOTS;
+    const unsigned int sgrid = (unsigned int)((ra.nslots + SS - 1) / SS);
     // both lists together hold at most C slots: ceil(nA/T) + ceil(nN/T) <= C/T + 2 blocks
     const unsigned int pgrid = (unsigned int)(ra.nslots / FMC_ROUND_PASS_THREADS + 2);
     return MB::dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
-      round_solve_kernel<M, decltype(J)::value><<<sgrid, FMC_ROUND_SOLVE_THREADS, 0, st>>>(ap, ra);
+      round_solve_kernel<M, decltype(J)::value><<<sgrid, ST, SolveCfg<M::NPARAM>::SMEM_BYTES, st>>>(ap, ra);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
       round_ctl_kernel<M><<<1, 32, 0, st>>>(ra, handle, use_handle);
@@ -407,8 +486,14 @@ struct RoundBinding {
   }
   static cudaError_t prepare(bool inject, bool smem, int jac, size_t shmem, int* nb) {
     return MB::dispatch(inject, smem, jac, [&](auto I, auto S, auto J) {
+      cudaError_t e = cudaSuccess;
+      if (SolveCfg<M::NPARAM>::SMEM_BYTES > 0) {
+        e = cudaFuncSetAttribute(round_solve_kernel<M, decltype(J)::value>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)SolveCfg<M::NPARAM>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+      }
       auto kern = round_pass_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>;
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
       if (e != cudaSuccess) return e;
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, kern, FMC_ROUND_PASS_THREADS, shmem);
     });

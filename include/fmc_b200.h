@@ -45,6 +45,7 @@ extern "C" {
 #define FMC_ERR_STATE (-6)       /* fmc_finish without a launch in flight */
 #define FMC_ERR_ALLOC (-7)       /* host or device allocation failed */
 #define FMC_ERR_NCCL (-8)        /* NCCL could not be loaded or an NCCL call failed */
+#define FMC_ERR_UNSUPPORTED (-9) /* an optional feature that this build of the library does not contain */
 
 #define FMC_MAX_PARAM 16
 #define FMC_DEFAULT_SEED 31415ULL /* the reference's seed, utils.f90:7 */
@@ -182,7 +183,9 @@ int fmc_model_has_analytic_jacobian(int model);
  * counter; the measured choice for the small fits of this path.
  * FMC_FIT_PER_WARP: one resample per warp -- the data points of a pass are split over the 32
  * lanes and the p x p sums combined by warp shuffles; meant for large ndata x nparam.
- * EXPERIMENTAL: same results up to summation order; not yet measured on a GPU (round 1).
+ * Measured on B200 (round 2, profiles/r2_mapping_*.json): 0.47-0.70 of the thread-per-fit rate on
+ * C4 (ndata 10^4, nparam 10) and 0.47 on C5, so it is NOT part of the default build
+ * (`make WARP=1` compiles it in); without it the call returns FMC_ERR_UNSUPPORTED.
  * ctx = NULL sets the mapping of the one-call entry points. */
 #define FMC_FIT_PER_THREAD 0
 #define FMC_FIT_PER_WARP 1
@@ -193,11 +196,16 @@ int fmc_set_fit_mapping(fmc_context* ctx, int mapping);
  * steps of its fit and takes the next fit from a counter when it ends.
  * FMC_SCHEDULE_ROUNDS: passes and solver steps in separate kernels that alternate inside a CUDA
  * graph WHILE node; fits that want another pass are compacted into lists between rounds
- * (DESIGN.md 2.8).  Same per-fit arithmetic, bit for bit; which one is faster depends on how
- * much the fits diverge (measured: DESIGN.md 2.8).  The default is FMC_SCHEDULE_REFILL unless the
- * environment variable FMC_SCHEDULE=rounds is set.  ctx = NULL sets it for the one-call entry points. */
+ * (DESIGN.md 2.8).  Same solver source and the same per-fit sequence of operations; the two compile it
+ * differently, so a small share of the fits differs in the last bits (tests/test_round_schedule.py).
+ * FMC_SCHEDULE_AUTO (default): by measurement -- rounds when the data rows do not fit in shared memory
+ * or nparam > 6 (C4: +19 %), refill otherwise (C1, C2).  Strongly diverging fits (C5: +19 % with rounds)
+ * cannot be recognised beforehand; choose FMC_SCHEDULE_ROUNDS for them.  The environment variable
+ * FMC_SCHEDULE=refill|rounds overrides the default.  ctx = NULL sets it for the one-call entry points.
+ * fmc_get_schedule returns the setting, or, for AUTO, what the last launch resolved it to. */
 #define FMC_SCHEDULE_REFILL 0
 #define FMC_SCHEDULE_ROUNDS 1
+#define FMC_SCHEDULE_AUTO 2
 int fmc_set_schedule(fmc_context* ctx, int schedule);
 int fmc_get_schedule(const fmc_context* ctx);
 

@@ -98,10 +98,13 @@ def test_host_image_of_the_solver_reaches_the_oracles_chi2_on_c5(emul, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mapping", ["thread", "warp"])
-def test_cuda_path_reaches_the_oracles_chi2_on_c5(oracle, mapping):
+@pytest.mark.parametrize("mapping,schedule", [("thread", "refill"), ("thread", "rounds"), ("warp", "refill")])
+def test_cuda_path_reaches_the_oracles_chi2_on_c5(oracle, mapping, schedule):
     import fitter_mc_b200 as fmc
 
+    if mapping == "warp" and fmc.lib().fmc_set_fit_mapping(None, 1) == -9:
+        pytest.skip("warp-per-fit kernels not in this build (make WARP=1)")
+    fmc.lib().fmc_set_fit_mapping(None, 0)
     model, x, y, err, start, z = _setup(oracle, 1000)
     want = oracle.bootstrap(model, x, y, err, start, len(z), z=z, flags=_oracle_flags(oracle), nthreads=8)
     zdev = None
@@ -111,6 +114,7 @@ def test_cuda_path_reaches_the_oracles_chi2_on_c5(oracle, mapping):
 
         ctx.set_data(model, x, y, err)
         ctx.set_fit_mapping(mapping)
+        ctx.set_schedule(schedule)
         zdev = torch.from_numpy(z).cuda()
         torch.cuda.synchronize()
         ctx.launch(start, len(z), z_inject_dev=zdev.data_ptr(), keep=True)
@@ -120,6 +124,7 @@ def test_cuda_path_reaches_the_oracles_chi2_on_c5(oracle, mapping):
         ctx.close()
     rc = got["counters"][:, 1, 0]
     passes = got["counters"][:, :, 4].sum(1)
+    mapping = mapping + "/" + schedule
     print("\n[c5 stress cuda/%s] return codes 3..10: gpu %s oracle %s ; passes per fit mean %.1f median %d p90 %d "
           "p99 %d max %d ; safety-cap hits %d"
           % (mapping, np.bincount(rc, minlength=11)[3:11].tolist(), want["rc_count"][3:11].tolist(), passes.mean(),

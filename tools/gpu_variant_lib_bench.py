@@ -15,11 +15,11 @@ import fitter_mc_b200.api as api
 api.lib_path = lambda: %(lib)r
 import fitter_mc_b200 as fmc, datasets, oracle_lib as oracle
 out = {}
-for name in ("c2",):
+for name in %(configs)r:
     model, x, y, err = datasets.dataset(name)
-    start, _ = oracle.fit_data(model, x, y, err, fmc.initialise_model(model)["params_init"])
+    start = datasets.C5_FITTED.copy() if name == "c5" else oracle.fit_data(model, x, y, err, fmc.initialise_model(model)["params_init"])[0]
     ctx = fmc.Context(0); ctx.set_data(model, x, y, err)
-    nres, best = 2000000, None
+    nres, best = {"c5": 400000, "c4": 100000}.get(name, 2000000), None
     for rep in range(4):
         ctx.launch(start, nres, first_counter=rep * nres); r = ctx.finish()
         ms = ctx.kernel_ms(); best = ms if best is None else min(best, ms)
@@ -32,7 +32,8 @@ print(json.dumps(out))
 def main():
     res = {}
     for lib in sys.argv[1:]:
-        p = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, lib=os.path.abspath(lib))],
+        configs = tuple(os.environ.get("FMC_VARIANT_CONFIGS", "c2").split(","))
+        p = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, lib=os.path.abspath(lib), configs=configs)],
                            capture_output=True, text=True)
         res[os.path.basename(lib)] = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else p.stderr[-800:]
     print(json.dumps(res, indent=1))
