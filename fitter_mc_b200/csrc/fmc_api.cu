@@ -880,12 +880,12 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     c->chunk_p = P;
   }
   const long long nchunks = (nresample + cap - 1) / cap;
-  if (2 * nchunks > c->ncounters) {
+  if (4 * nchunks > c->ncounters) {  // one work counter per persistent launch: 2 halves x 2 nl2sno calls per chunk
     cudaFree(c->counters_dev);
     c->counters_dev = nullptr;
     c->ncounters = 0;
-    FMC_CUDA(cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * 2 * nchunks));
-    c->ncounters = (int)(2 * nchunks);
+    FMC_CUDA(cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * 4 * nchunks));
+    c->ncounters = (int)(4 * nchunks);
   }
 
   KernelArgs a;
@@ -1008,7 +1008,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     if (prc != FMC_OK) return prc;
     c->rs_used = true;
   }
-  if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 2 * nchunks, c->stream));
+  if (nchunks > 0) FMC_CUDA(cudaMemsetAsync(c->counters_dev, 0, sizeof(unsigned long long) * 4 * nchunks, c->stream));
   FMC_CUDA(cudaMemsetAsync(c->acc, 0, sizeof(double) * acc_len(P, Q), c->stream));
   FMC_CUDA(cudaMemsetAsync(c->anom_dev, 0, sizeof(unsigned long long) * (1 + 2 * fmc::ANOM_CAP), c->stream));
   if (binning)
@@ -1043,7 +1043,7 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
       // as below), then rounds of solve / pass over the slot pool until every fit of the chunk has
       // been through both nl2sno calls, then the moment sums
       a.call = 0;
-      a.next_id = c->counters_dev + 2 * ch;
+      a.next_id = c->counters_dev + 4 * ch;
       if (shared_init)
         FMC_LAUNCH(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
       else
@@ -1057,12 +1057,15 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
     }
     if (per_warp) {
       a.call = 0;
-      a.next_id = c->counters_dev + 2 * ch;
+      a.next_id = c->counters_dev + 4 * ch;
       FMC_LAUNCH(wentry.launch(a, wa, inject, jac, (int)grid, shmem, c->stream));
     }
+    // Refill schedule.  (Running the two halves of a chunk on two streams, so that the blocks of one half's
+    // persistent kernel fill the tail of the other's, was measured and is SLOWER: C2 2.49e7 against 2.69e7
+    // fits/s, C5 5.84e5 against 6.96e5 -- profiles/r2_refill_split_streams.json.)
     for (int call = 0; call < 2 && !per_warp && !rounds; ++call) {  // fit_data: nl2sno twice (bootstrap.f90:219-225)
       a.call = call;
-      a.next_id = c->counters_dev + 2 * ch + call;
+      a.next_id = c->counters_dev + 4 * ch + call;
       if (call == 0 && shared_init)
         FMC_LAUNCH(m.launch_init_shared(a, c->rowj_dev, g0_dev, inject, shmem_shared, c->stream));
       else

@@ -4,7 +4,11 @@
 // The solver is compiled with rolled loops and out-of-line helpers here (nl2_solver.cuh, FMC_SOLVER_ROLLED):
 // the solve kernel keeps its state in shared (or local) memory where dynamic indexing costs nothing, and
 // what it is short of is instruction cache.  No other kernel of this translation unit contains solver code.
+#if !defined(FMC_ROUND_SOLVER_UNROLLED)
 #define FMC_SOLVER_ROLLED 1
+#else
+#define FMC_SOLVER_OUTLINE 1  // (experiment: unrolled loops, out-of-line helpers)
+#endif
 #include "models/model_user.cuh"
 #include "models/models_bench.cuh"
 #include "round_kernels.cuh"

@@ -43,149 +43,71 @@
 // 20 000-instruction solver).  In that mode the small dense helpers -- inlined at some fifty call sites,
 // each with its copy of the FP64 square root and of v2norm's overflow-safe fallback -- become real
 // functions (FMC_SOLVER_FN).
+#if defined(FMC_SOLVER_ROLLED) && !defined(FMC_SOLVER_OUTLINE)
+#define FMC_SOLVER_OUTLINE 1
+#endif
 #if defined(FMC_SOLVER_ROLLED) && defined(__CUDACC__)
 #define FMC_SOLVER_LOOP _Pragma("unroll 1")
-#define FMC_SOLVER_FN inline __noinline__
 #else
 #define FMC_SOLVER_LOOP
+#endif
+#if defined(FMC_SOLVER_OUTLINE) && defined(__CUDACC__)
+#define FMC_SOLVER_FN inline __noinline__
+#else
 #define FMC_SOLVER_FN inline
 #endif
 
 namespace fmc {
 
 // ----------------------------------------------------------------- small dense helpers
-FMC_HD FMC_INLINE double dotn(int n, const double* x, const double* y) {  // dotprd, toms573.f90:2403
-  double s = 0.0;
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < n; ++i) s += x[i] * y[i];
-  return s;
-}
-
-// v2norm (toms573.f90:4789-4838).  The reference's scaled recurrence (one divide per element)
-// only exists to dodge overflow/underflow of the squares; for p-vectors in the normal range
-// sqrt(sum x^2) is the same number to within an ulp, so that is what is evaluated, and the
-// scaled recurrence is kept as the fallback when the plain sum leaves the normal range.
-FMC_HD inline double nrm2_scaled(int n, const double* x) {
-  int i = 0;
-  FMC_SOLVER_LOOP
-  for (; i < n; ++i)
-    if (x[i] != 0.0) break;
-  if (i >= n) return 0.0;
-  double scale = fabs(x[i]);
-  if (i == n - 1) return scale;
-  double t = 1.0;
-  FMC_SOLVER_LOOP
-  for (int j = i + 1; j < n; ++j) {
-    double xi = fabs(x[j]);
-    if (!(xi > scale)) {
-      double r = xi / scale;
-      if (r > k::sqteta) t = t + r * r;
-    } else {
-      double r = scale / xi;
-      if (r <= k::sqteta) r = 0.0;
-      t = 1.0 + t * r * r;
-      scale = xi;
-    }
-  }
-  return scale * sqrt(t);
-}
-#if defined(FMC_SOLVER_ROLLED) && defined(__CUDACC__)
-FMC_HD FMC_SOLVER_FN double nrm2(int n, const double* x) {
+// (nl2_dense.inc) dotn, nrm2, ltsolve_t, ltsolve, chol_rows, symv -- the flavour of the common path ...
+#define FMC_DENSE_NAME(f) f
+#define FMC_DENSE_LOOP FMC_SOLVER_LOOP
+#define FMC_DENSE_ATTR FMC_SOLVER_FN
+#if defined(FMC_SOLVER_OUTLINE) && defined(__CUDACC__)
+#define FMC_DENSE_ATTR_SMALL FMC_INLINE
+#define FMC_DENSE_ATTR_SMALL_OL FMC_SOLVER_FN
 #else
-FMC_HD FMC_INLINE double nrm2(int n, const double* x) {
+#define FMC_DENSE_ATTR_SMALL FMC_INLINE
+#define FMC_DENSE_ATTR_SMALL_OL FMC_INLINE
 #endif
-  double s = 0.0;
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < n; ++i) s = fma(x[i], x[i], s);
-  if (s > 1e-280 && s < 1e280) return sqrt(s);
-  return nrm2_scaled(n, x);
-}
-
-// Solve (L**T) x = y, L packed lower-by-rows (litvmu, toms573.f90:3334).
-FMC_HD FMC_SOLVER_FN void ltsolve_t(int n, double* x, const double* l, const double* y) {
-  FMC_SOLVER_LOOP
-  for (int i = 0; i < n; ++i) x[i] = y[i];
-  int i0 = n * (n + 1) / 2;
-  FMC_SOLVER_LOOP
-  for (int i = n; i >= 1; --i) {
-    double xi = x[i - 1] / l[i0 - 1];
-    x[i - 1] = xi;
-    if (i <= 1) return;
-    i0 -= i;
-    if (xi == 0.0) continue;
-    FMC_SOLVER_LOOP
-    for (int j = 1; j <= i - 1; ++j) x[j - 1] -= xi * l[i0 + j - 1];
-  }
-}
-
-// Solve L x = y (livmul, toms573.f90:3367).
-FMC_HD FMC_SOLVER_FN void ltsolve(int n, double* x, const double* l, const double* y) {
-  int kk = 1;
-  FMC_SOLVER_LOOP
-  for (; kk <= n; ++kk) {
-    if (y[kk - 1] != 0.0) break;
-    x[kk - 1] = 0.0;
-  }
-  if (kk > n) return;
-  int j = kk * (kk + 1) / 2;
-  x[kk - 1] = y[kk - 1] / l[j - 1];
-  FMC_SOLVER_LOOP
-  for (int i = kk + 1; i <= n; ++i) {
-    double t = dotn(i - 1, &l[j], x);
-    j += i;
-    x[i - 1] = (y[i - 1] - t) / l[j - 1];
-  }
-}
-
-// Cholesky factor by rows, packed (lsqrt, toms573.f90:3842).  Returns 0 or the index of
-// the first non-positive reduced diagonal (stored in place of the diagonal).
-FMC_HD FMC_SOLVER_FN int chol_rows(int n, double* l, const double* a) {
-  int i0 = 0;
-  FMC_SOLVER_LOOP
-  for (int i = 1; i <= n; ++i) {
-    double td = 0.0;
-    int j0 = 0;
-    FMC_SOLVER_LOOP
-    for (int j = 1; j <= i - 1; ++j) {
-      double t = 0.0;
-      FMC_SOLVER_LOOP
-      for (int m = 1; m <= j - 1; ++m) t += l[i0 + m - 1] * l[j0 + m - 1];
-      j0 += j;
-      t = (a[i0 + j - 1] - t) / l[j0 - 1];
-      l[i0 + j - 1] = t;
-      td += t * t;
-    }
-    i0 += i;
-    double t = a[i0 - 1] - td;
-    if (t <= 0.0) {
-      l[i0 - 1] = t;
-      return i;
-    }
-    l[i0 - 1] = sqrt(t);
-  }
-  return 0;
-}
-
-// y = S x for packed lower-by-rows symmetric S (slvmul, toms573.f90:4697).
-FMC_HD FMC_SOLVER_FN void symv(int p, double* y, const double* s, const double* x) {
-  int j = 0;
-  FMC_SOLVER_LOOP
-  for (int i = 1; i <= p; ++i) {
-    y[i - 1] = dotn(i, &s[j], x);
-    j += i;
-  }
-  j = 0;
-  FMC_SOLVER_LOOP
-  for (int i = 2; i <= p; ++i) {
-    double xi = x[i - 1];
-    j += 1;
-    FMC_SOLVER_LOOP
-    for (int m = 1; m <= i - 1; ++m) {
-      y[m - 1] += s[j] * xi;
-      j += 1;
-    }
-  }
-}
+#include "nl2_dense.inc"
+#undef FMC_DENSE_NAME
+#undef FMC_DENSE_LOOP
+#undef FMC_DENSE_ATTR
+#undef FMC_DENSE_ATTR_SMALL
+#undef FMC_DENSE_ATTR_SMALL_OL
+// ... and the flavour of the RARE, long-running paths: names f_r, used by gqtstp, lsvmin and the
+// More-Hebden iterations of lmstep.  In the refill kernel (FMC_SOLVER_RARE_ROLLED, kernels_model*.cu) the
+// common path -- assess, the secant update, factor, the Gauss-Newton part of a step -- stays unrolled and
+// inlined, which is what a well-behaved fit executes (C1, C2), while these paths and all loops of lmstep
+// are rolled, with the helpers as real functions: 21 800 -> 13 300 instructions for p = 4.  Measured
+// (profiles/r2_refill_solver_flavours.json): C5 +31 % (4.39e5 -> 5.75e5 fits/s), C2 +0.2 %, C1 -5 %;
+// rolling everything gives C5 +48 % but C2 -3 % and C1 -30 %; rolling factor/adopt_jacobian too, C1 -17 %.
+#if defined(FMC_SOLVER_RARE_ROLLED) && !defined(FMC_SOLVER_ROLLED) && defined(__CUDACC__)
+#define FMC_RARE_LOOP _Pragma("unroll 1")
+#define FMC_RARE_FN __noinline__
+#define FMC_DENSE_NAME(f) f##_r
+#define FMC_DENSE_LOOP _Pragma("unroll 1")
+#define FMC_DENSE_ATTR inline __noinline__
+#define FMC_DENSE_ATTR_SMALL inline __noinline__
+#define FMC_DENSE_ATTR_SMALL_OL inline __noinline__
+#include "nl2_dense.inc"
+#undef FMC_DENSE_NAME
+#undef FMC_DENSE_LOOP
+#undef FMC_DENSE_ATTR
+#undef FMC_DENSE_ATTR_SMALL
+#undef FMC_DENSE_ATTR_SMALL_OL
+#else
+#define FMC_RARE_LOOP FMC_SOLVER_LOOP
+#define FMC_RARE_FN
+#define dotn_r dotn
+#define nrm2_r nrm2
+#define ltsolve_t_r ltsolve_t
+#define ltsolve_r ltsolve
+#define chol_rows_r chol_rows
+#define symv_r symv
+#endif
 
 // ----------------------------------------------------------------- the solver
 enum Nl2Phase { PH_INIT = 0, PH_TRIAL = 1, PH_JAC = 2 };
@@ -771,7 +693,7 @@ L20:
   v[DST0] = -1.0;
   if (ierr != 0) goto L50;
   ltsolve_t(p, w, hmat, qtr);
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     st[i] = dd[j1] * ww[i];
@@ -781,7 +703,7 @@ L20:
   phi = dst - rad;
   if (phi <= phimax) goto L350;
   if (ka > 0) goto L70;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     st[i] = dd[j1] * (st[i] / dst);
@@ -791,7 +713,7 @@ L20:
   ww[phipin] = (t / dst) * t;
   lk = phi * ww[phipin];
 L50:
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) ww[i] = gg[i] / dd[i];
   v[DGNORM] = nrm2(p, w);
   uk = v[DGNORM] / rad;
@@ -803,16 +725,16 @@ L70:
     goto L370;
   }
   ka = ka + 1;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 0; i < pp1o2; ++i) ww[rmat + i] = hmat[i];
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 0; i < p; ++i) ww[res + i] = qtr[i];
   if (alphak <= 0.0 || alphak < lk || alphak >= uk) alphak = uk * fmax(p001, sqrt(lk / uk));
   sqrtak = sqrt(alphak);
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) ww[i] = 1.0;
 
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     l = i * (i + 1) / 2 + rmat0;
     wl = ww[l];
@@ -830,7 +752,7 @@ L70:
     d2 = d2 / t;
     ww[l] = t * wl;
     a = -a;
-    FMC_SOLVER_LOOP
+    FMC_RARE_LOOP
     for (j1 = i; j1 <= p; ++j1) {
       l = l + j1;
       st[j1] = a * ww[l];
@@ -844,7 +766,7 @@ L70:
     ww[i] = d2 / t;
     d2 = d1 / t;
     ww[l] = t * adi;
-    FMC_SOLVER_LOOP
+    FMC_RARE_LOOP
     for (j1 = i; j1 <= p; ++j1) {
       l = l + j1;
       wl = ww[l];
@@ -854,7 +776,7 @@ L70:
   L130:
     if (i == p) goto L240;
     ip1 = i + 1;
-    FMC_SOLVER_LOOP
+    FMC_RARE_LOOP
     for (i1 = ip1; i1 <= p; ++i1) {
       l = i1 * (i1 + 1) / 2 + rmat0;
       wl = ww[l];
@@ -864,7 +786,7 @@ L70:
       d1 = d1 * dfacsq;
       wl = wl / dfac;
       kk = l;
-      FMC_SOLVER_LOOP
+      FMC_RARE_LOOP
       for (j1 = i1; j1 <= p; ++j1) {
         kk = kk + j1;
         ww[kk] = ww[kk] / dfac;
@@ -880,7 +802,7 @@ L70:
       ww[l] = t * wl;
       ww[i1] = d1 / t;
       d2 = d2 / t;
-      FMC_SOLVER_LOOP
+      FMC_RARE_LOOP
       for (j1 = i1; j1 <= p; ++j1) {
         l = l + j1;
         wl = ww[l];
@@ -897,7 +819,7 @@ L70:
       ww[i1] = d2 / t;
       d2 = d1 / t;
       ww[l] = t * si;
-      FMC_SOLVER_LOOP
+      FMC_RARE_LOOP
       for (j1 = i1; j1 <= p; ++j1) {
         l = l + j1;
         wl = ww[l];
@@ -908,13 +830,13 @@ L70:
     L200:
       if (d2 >= dtol) continue;
       d2 = d2 * dfacsq;
-      FMC_SOLVER_LOOP
+      FMC_RARE_LOOP
       for (kk = i1; kk <= p; ++kk) st[kk] = st[kk] / dfac;
     }
   }
 L240:
-  ltsolve_t(p, &ww[res], &ww[rmat], &ww[res]);
-  FMC_SOLVER_LOOP
+  ltsolve_t_r(p, &ww[res], &ww[rmat], &ww[res]);
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     kk = res0 + i;
@@ -922,14 +844,14 @@ L240:
     st[j1] = -t;
     ww[kk] = t * dd[j1];
   }
-  dst = nrm2(p, &ww[res]);
+  dst = nrm2_r(p, &ww[res]);
   phi = dst - rad;
   if (phi <= phimax && phi >= phimin) goto L370;
   if (oldphi == phi) goto L370;
   oldphi = phi;
   if (phi > 0.0) goto L270;
   if (ka >= kalim) goto L370;
-  twopsi = alphak * dst * dst - dotn(p, step, g);
+  twopsi = alphak * dst * dst - dotn_r(p, step, g);
   if (alphak >= twopsi * psifac) goto L270;
   v[STPPAR] = -alphak;
   goto L380;
@@ -939,16 +861,16 @@ L260:
 L270:
   if (phi < 0.0) uk = alphak;
 L280:
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     kk = res0 + i;
     st[i] = dd[j1] * (ww[kk] / dst);
   }
-  ltsolve(p, step, &ww[rmat], step);
-  FMC_SOLVER_LOOP
+  ltsolve_r(p, step, &ww[rmat], step);
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) st[i] = st[i] / sqrt(ww[i]);
-  t = 1.0 / nrm2(p, step);
+  t = 1.0 / nrm2_r(p, step);
   alphak = alphak + t * phi * t / rad;
   lk = fmax(lk, alphak);
   goto L70;
@@ -977,12 +899,12 @@ L330:
   uk = 0.0;
   v[GTSTEP] = 0.0;
   v[PREDUC] = 0.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) st[i] = 0.0;
   goto L390;
 L350:
   alphak = 0.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j1 = ipiv[i];
     st[j1] = -ww[i];
@@ -1002,20 +924,20 @@ L390:
 
 // lsvmin (toms573.f90:3896-4047): over-estimate of the smallest singular value of L.
 template <int P>
-FMC_HD double Nl2<P>::lsvmin(const double* l_, double* x_, double* y_) {
+FMC_HD FMC_RARE_FN double Nl2<P>::lsvmin(const double* l_, double* x_, double* y_) {
   const double* l = l_ - 1;
   double* xv = x_ - 1;
   double* yv = y_ - 1;
   const int p = P;
   int ii = 0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (int i = 1; i <= p; ++i) {
     xv[i] = 0.0;
     ii += i;
     if (l[ii] == 0.0) return 0.0;
   }
   if (lsvmin_ix % 9973 == 0) lsvmin_ix = 2;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (int j = p; j >= 1; --j) {
     lsvmin_ix = (3432 * lsvmin_ix) % 9973;
     double b = 0.5 * (1.0 + (double)lsvmin_ix / 9973.0);
@@ -1028,34 +950,34 @@ FMC_HD double Nl2<P>::lsvmin(const double* l_, double* x_, double* y_) {
     int jj = j0 + j;
     xplus = xplus / l[jj];
     xminus = xminus / l[jj];
-    FMC_SOLVER_LOOP
+    FMC_RARE_LOOP
     for (int i = 1; i <= jm1; ++i) {
       splus += fabs(xv[i] + l[j0 + i] * xplus);
       sminus += fabs(xv[i] + l[j0 + i] * xminus);
     }
     if (sminus > splus) xplus = xminus;
     xv[j] = xplus;
-    FMC_SOLVER_LOOP
+    FMC_RARE_LOOP
     for (int i = 1; i <= jm1; ++i) xv[i] += l[j0 + i] * xplus;
   }
-  double t = 1.0 / nrm2(p, x_);
-  FMC_SOLVER_LOOP
+  double t = 1.0 / nrm2_r(p, x_);
+  FMC_RARE_LOOP
   for (int i = 1; i <= p; ++i) xv[i] = t * xv[i];
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (int j = 1; j <= p; ++j) {
     double psj = 0.0;
     int j0 = j * (j - 1) / 2;
-    FMC_SOLVER_LOOP
+    FMC_RARE_LOOP
     for (int i = 1; i <= j - 1; ++i) psj += l[j0 + i] * yv[i];
     yv[j] = (xv[j] - psj) / l[j0 + j];
   }
-  return 1.0 / nrm2(p, y_);
+  return 1.0 / nrm2_r(p, y_);
 }
 
 // ----------------------------------------------------------------- gqtstp
 // Goldfeld-Quandt-Trotter step for the augmented model (toms573.f90:2471-3039).
 template <int P>
-FMC_HD void Nl2<P>::gqtstp() {
+FMC_HD FMC_RARE_FN void Nl2<P>::gqtstp() {
   const double* dd = d - 1;
   const double* dg = dig - 1;
   double* dihdi = hmat - 1;
@@ -1110,29 +1032,29 @@ FMC_HD void Nl2<P>::gqtstp() {
   ka = 0;
   kalim = 50;
   j = 0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j += i;
     ww[diag0 + i] = dihdi[j];
   }
   t1 = 0.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= PP; ++i) {
     t = fabs(dihdi[i]);
     if (t1 < t) t1 = t;
   }
   ww[dggdmx] = t1;
 L30:
-  irc_ = chol_rows(p, lmat, hmat);
+  irc_ = chol_rows_r(p, lmat, hmat);
   if (irc_ == 0) goto L50;
   j = irc_ * (irc_ + 1) / 2;
   t = l[j];
   l[j] = 1.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= irc_; ++i) ww[i] = 0.0;
   ww[irc_] = 1.0;
-  ltsolve_t(irc_, w, lmat, w);
-  t1 = nrm2(irc_, w);
+  ltsolve_t_r(irc_, w, lmat, w);
+  t1 = nrm2_r(irc_, w);
   lk = -t / t1 / t1;
   v[DST0] = -lk;
   if (restrt) goto L200;
@@ -1140,25 +1062,25 @@ L30:
   goto L60;
 L50:
   lk = 0.0;
-  ltsolve(p, &ww[q], lmat, dig);
-  v[NREDUC] = 0.5 * dotn(p, &ww[q], &ww[q]);
-  ltsolve_t(p, &ww[q], lmat, &ww[q]);
+  ltsolve_r(p, &ww[q], lmat, dig);
+  v[NREDUC] = 0.5 * dotn_r(p, &ww[q], &ww[q]);
+  ltsolve_t_r(p, &ww[q], lmat, &ww[q]);
   have_q = true;
-  dst = nrm2(p, &ww[q]);
+  dst = nrm2_r(p, &ww[q]);
   v[DST0] = dst;
   phi = dst - rad;
   if (phi <= phimax) goto L260;
   if (restrt) goto L200;
 L60:
-  v[DGNORM] = nrm2(p, dig);
+  v[DGNORM] = nrm2_r(p, dig);
   if (v[DGNORM] == 0.0) goto L430;
   kk = 0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     wi = 0.0;
     if (i != 1) {
       im1 = i - 1;
-      FMC_SOLVER_LOOP
+      FMC_RARE_LOOP
       for (j = 1; j <= im1; ++j) {
         kk = kk + 1;
         t = fabs(dihdi[kk]);
@@ -1171,7 +1093,7 @@ L60:
   }
   kk = 1;
   t1 = ww[diag] - ww[1];
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 2; i <= p; ++i) {
     j = diag0 + i;
     t = ww[j] - ww[i];
@@ -1185,7 +1107,7 @@ L60:
   k1 = kk * (kk - 1) / 2 + 1;
   inc = 1;
   t = 0.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     if (i == kk) goto L120;
     aki = fabs(dihdi[k1]);
@@ -1204,7 +1126,7 @@ L60:
   uk = v[DGNORM] / rad - ww[emin];
   kk = 1;
   t1 = ww[diag] + ww[1];
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 2; i <= p; ++i) {
     j = diag0 + i;
     t = ww[j] + ww[i];
@@ -1218,7 +1140,7 @@ L60:
   k1 = kk * (kk - 1) / 2 + 1;
   inc = 1;
   t = 0.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     if (i == kk) goto L170;
     aki = fabs(dihdi[k1]);
@@ -1237,8 +1159,8 @@ L60:
   lk = fmax(lk, v[DGNORM] / rad - ww[emax]);
   alphak = fabs(v[STPPAR]) * v[RAD0] / rad;
   if (irc_ != 0) goto L200;
-  ltsolve(p, w, lmat, &ww[q]);
-  t = nrm2(p, w);
+  ltsolve_r(p, w, lmat, &ww[q]);
+  t = nrm2_r(p, w);
   ww[phipin] = dst / t / t;
   lk = fmax(lk, phi * ww[phipin]);
 L200:
@@ -1250,29 +1172,29 @@ L200:
   ka = ka + 1;
   if (-v[DST0] >= alphak || alphak < lk || alphak >= uk) alphak = uk * fmax(p001, sqrt(lk / uk));
   kk = 0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     kk = kk + i;
     dihdi[kk] = ww[diag0 + i] + alphak;
   }
-  irc_ = chol_rows(p, lmat, hmat);
+  irc_ = chol_rows_r(p, lmat, hmat);
   if (irc_ == 0) goto L230;
   j = (irc_ * (irc_ + 1)) / 2;
   t = l[j];
   l[j] = 1.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= irc_; ++i) ww[i] = 0.0;
   ww[irc_] = 1.0;
-  ltsolve_t(irc_, w, lmat, w);
-  t1 = nrm2(irc_, w);
+  ltsolve_t_r(irc_, w, lmat, w);
+  t1 = nrm2_r(irc_, w);
   lk = alphak - t / t1 / t1;
   v[DST0] = -lk;
   goto L200;
 L230:
-  ltsolve(p, &ww[q], lmat, dig);
-  ltsolve_t(p, &ww[q], lmat, &ww[q]);
+  ltsolve_r(p, &ww[q], lmat, dig);
+  ltsolve_t_r(p, &ww[q], lmat, &ww[q]);
   have_q = true;
-  dst = nrm2(p, &ww[q]);
+  dst = nrm2_r(p, &ww[q]);
   phi = dst - rad;
   if (phi <= phimax && phi >= phimin) goto L270;
   if (phi == oldphi) goto L270;
@@ -1280,12 +1202,12 @@ L230:
   if (phi > 0.0) goto L240;
   if (v[DST0] > 0.0) goto L240;
   delta = alphak + v[DST0];
-  twopsi = alphak * dst * dst + dotn(p, dig, &ww[q]);
+  twopsi = alphak * dst * dst + dotn_r(p, dig, &ww[q]);
   if (delta < psifac * twopsi) goto L250;
 L240:
   if (ka >= kalim) goto L270;
-  ltsolve(p, w, lmat, &ww[q]);
-  t1 = nrm2(p, w);
+  ltsolve_r(p, w, lmat, &ww[q]);
+  t1 = nrm2_r(p, w);
   if (phi < 0.0) uk = fmin(uk, alphak);
   alphak = alphak + (phi / t1) * (dst / t1) * (dst / rad);
   lk = fmax(lk, alphak);
@@ -1296,9 +1218,9 @@ L250:
 L260:
   alphak = 0.0;
 L270:
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) st[i] = -ww[q0 + i] / dd[i];
-  v[GTSTEP] = -dotn(p, dig, &ww[q]);
+  v[GTSTEP] = -dotn_r(p, dig, &ww[q]);
   v[PREDUC] = 0.5 * (fabs(alphak) * dst * dst - v[GTSTEP]);
   goto L410;
 L290:
@@ -1306,7 +1228,7 @@ L290:
   restrt = true;
   ka = ka + 1;
   kk = 0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     kk = kk + i;
     dihdi[kk] = ww[diag0 + i];
@@ -1340,42 +1262,42 @@ L330:
   t = lsvmin(lmat, &ww[xx], w);
   kk = 0;
 L340:
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) ww[i] = t * ww[i];
-  ltsolve_t(p, w, lmat, w);
-  t1 = 1.0 / nrm2(p, w);
+  ltsolve_t_r(p, w, lmat, w);
+  t1 = 1.0 / nrm2_r(p, w);
   t = t1 * t;
   if (t <= delta) goto L370;
   if (kk > 30) goto L270;
   kk = kk + 1;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) ww[x00 + i] = t1 * ww[i];
-  ltsolve(p, w, lmat, &ww[xx]);
-  t = 1.0 / nrm2(p, w);
+  ltsolve_r(p, w, lmat, &ww[xx]);
+  t = 1.0 / nrm2_r(p, w);
   goto L340;
 L370:
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) ww[i] = t1 * ww[i];
-  sw = dotn(p, &ww[q], w);
+  sw = dotn_r(p, &ww[q], w);
   t1 = (rad + dst) * (rad - dst);
   root = sqrt(sw * sw + t1);
   if (sw < 0.0) root = -root;
   si = t1 / (sw + root);
   v[PREDUC] = 0.5 * twopsi;
   t1 = 0.0;
-  t = si * (alphak * sw - 0.5 * si * (alphak + t * dotn(p, &ww[xx], w)));
+  t = si * (alphak * sw - 0.5 * si * (alphak + t * dotn_r(p, &ww[xx], w)));
   if (t < epso6 * twopsi) goto L390;
   v[PREDUC] = v[PREDUC] + t;
   dst = rad;
   t1 = -si;
 L390:
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j = q0 + i;
     ww[j] = t1 * ww[i] - ww[j];
     st[i] = ww[j] / dd[i];
   }
-  v[GTSTEP] = dotn(p, dig, &ww[q]);
+  v[GTSTEP] = dotn_r(p, dig, &ww[q]);
 L410:
   v[DSTNRM] = dst;
   v[STPPAR] = alphak;
@@ -1384,7 +1306,7 @@ L410:
   v[RAD0] = rad;
   ww[dstsav] = dst;
   j = 0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) {
     j += i;
     dihdi[j] = ww[diag0 + i];
@@ -1395,7 +1317,7 @@ L430:
   v[PREDUC] = 0.0;
   v[DSTNRM] = 0.0;
   v[GTSTEP] = 0.0;
-  FMC_SOLVER_LOOP
+  FMC_RARE_LOOP
   for (i = 1; i <= p; ++i) st[i] = 0.0;
 }
 
