@@ -88,11 +88,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None  # the timed region (perf_counter): only rows that arrive inside it count
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -101,7 +102,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -114,7 +121,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.05)]
+        if not inside:  # a timed region shorter than the sampling period: the nearest sample
+            inside = [r for t, r in self.rows[-1:]]
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -353,20 +363,24 @@ def main():
             dist.all_reduce(sync_token)
         torch.cuda.synchronize()
 
+    # nvidia-smi takes a while to deliver its first sample: started before the warm-up, counted only
+    # inside the timed region (20 ms period)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     t0 = time.perf_counter()
     first_ms = device_step(0)
     t_first_step = time.perf_counter() - t0
     for w in range(1, args.warmup):
         device_step(w)
 
-    sampler = ClockSampler(local_rank)
     sync_all()
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     t_wall0 = time.perf_counter()
     ms = [device_step(args.warmup + k) for k in range(args.steps)]
     sync_all()
     t_wall = time.perf_counter() - t_wall0
+    sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = float(sum(ms))
     kernel_ms = ctx.kernel_ms()
