@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(FMC_THREADS, FMC_MIN_BLOCKS) iterate_kernel(co
 
   Nl2<P> s;
   s.anomaly = 0;
+  s.spec = 1;  // a trial pass of this kernel always evaluates the Jacobian too: lanes of a warp make their passes together
   double msum[NM], mcmp[NM];
 #pragma unroll
   for (int i = 0; i < NM; ++i) {

@@ -349,7 +349,7 @@ static int rounds_prepare(fmc_context* c, const fmc::RoundEntry& re, int P, bool
     c->rs_slot_cap = 0;
     FMC_CUDA(cudaMalloc(&c->rs.slot_fit, sizeof(long long) * slots));
     FMC_CUDA(cudaMalloc(&c->rs.slot_meta, sizeof(int) * 2 * slots));
-    FMC_CUDA(cudaMalloc(&c->rs.list, sizeof(int) * 4 * slots));
+    FMC_CUDA(cudaMalloc(&c->rs.list, sizeof(int) * 2 * fmc::RC_KINDS * slots));
     c->rs_slot_cap = slots;
   }
   if (!c->rs.ctl) {
@@ -368,11 +368,16 @@ static int rounds_prepare(fmc_context* c, const fmc::RoundEntry& re, int P, bool
     c->rs_kargs_cap = nchunks;
   }
   c->rs.nslots = slots;
+  // Residual sum first (Nl2::spec = 0) where a Jacobian row is expensive next to the model value -- many
+  // parameters -- and the passes are what a round costs; with few parameters the extra solve-kernel visit
+  // of every accepted step costs more than the Jacobians saved (measured: DESIGN.md 2.8).
+  c->rs.spec = P > 6 ? 0 : 1;
+  if (const char* e = std::getenv("FMC_ROUND_SPECULATE")) c->rs.spec = (e[0] == '0') ? 0 : 1;
   FMC_CUDA(cudaMemsetAsync(c->rs.ctl, 0, sizeof(unsigned int) * fmc::RC_NWORDS, c->stream));
   c->rs_rounds = 0;
 
   // the WHILE graph: body = one round; rebuilt only when what it was captured for changes
-  const long long key[8] = {c->model, (inject ? 1 : 0) | (smem ? 2 : 0) | (jac << 2), (long long)shmem, slots,
+  const long long key[8] = {c->model, (inject ? 1 : 0) | (smem ? 2 : 0) | (jac << 2) | (c->rs.spec << 4), (long long)shmem, slots,
                             (long long)(size_t)c->rs.state, (long long)(size_t)c->rs.slot_fit,
                             (long long)(size_t)c->rs.list, (long long)(size_t)c->rs_kargs_dev};
   (void)P;
@@ -1150,8 +1155,8 @@ int fmc_finish(fmc_context* c, double* sum_p, double* sum_p2, double* sum_prop, 
     FMC_CUDA(cudaMemcpyAsync(c->rs_ctl_pinned, c->rs.ctl, sizeof(unsigned int) * fmc::RC_NWORDS, cudaMemcpyDeviceToHost,
                              c->stream));
   FMC_CUDA(cudaStreamSynchronize(c->stream));
-  if (c->rs_used) {  // three kernels per round (solve, control, pass), counted on the device
-    c->nlaunch += 3LL * c->rs_ctl_pinned[fmc::RC_ROUNDS_TOTAL];
+  if (c->rs_used) {  // the kernels of the rounds (solve, control, pass [, residual-only]), counted on the device
+    c->nlaunch += (c->rs.spec ? 3LL : 4LL) * c->rs_ctl_pinned[fmc::RC_ROUNDS_TOTAL];
     c->rs_used = false;
     if (c->rs_ctl_pinned[fmc::RC_ERROR] != 0u) {
       c->inflight = -1;
@@ -1176,8 +1181,19 @@ int fmc_wait(fmc_context* c) {
   if (c->inflight < 0) return FMC_ERR_STATE;
   DeviceGuard guard_(c->device);
   FMC_CUDA(guard_.err);
+  if (c->rs_used)
+    FMC_CUDA(cudaMemcpyAsync(c->rs_ctl_pinned, c->rs.ctl, sizeof(unsigned int) * fmc::RC_NWORDS, cudaMemcpyDeviceToHost,
+                             c->stream));
   FMC_CUDA(cudaStreamSynchronize(c->stream));
   c->inflight = -1;
+  if (c->rs_used) {  // the kernels of the rounds (solve, control, pass [, residual-only]), counted on the device
+    c->nlaunch += (c->rs.spec ? 3LL : 4LL) * c->rs_ctl_pinned[fmc::RC_ROUNDS_TOTAL];
+    c->rs_used = false;
+    if (c->rs_ctl_pinned[fmc::RC_ERROR] != 0u) {
+      g_last_cuda_error = "round schedule: fits still iterating after the cap on rounds";
+      return FMC_ERR_CUDA;
+    }
+  }
   return FMC_OK;
 }
 

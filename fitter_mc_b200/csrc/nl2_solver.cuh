@@ -130,6 +130,13 @@ struct Nl2 {
   double res_G[PP];   // J(x)^T J(x), lower triangle by rows
   double res_lky[P];  // J(x0)^T r(x)
   int need_b;
+  // Whether a trial point is evaluated with its Jacobian right away (spec = 1: an accepted step, the
+  // normal case of a well-behaved fit, then needs no second pass) or with the residual sum alone first
+  // (spec = 0: need_jac = 0 for the trial pass; only an accepted step that does not end the call asks
+  // for the Jacobian pass, through the same path as a step that assess moved back to an earlier trial
+  // point).  The solver takes the same decisions on the same numbers either way; what changes is how
+  // many passes compute a Jacobian nobody reads -- rejected steps and the last step of every call.
+  int spec, need_jac;
 
   // ---- NL2SOL state (names follow the reference's iv/v maps)
   double step[P], stlstg[P], d[P], g[P], dig[P], lky[P], tmp1[P], tmp2[P], qtr[P];
@@ -158,6 +165,7 @@ struct Nl2 {
     mlstgd = 0;
     lsvmin_ix = 2;
     anomaly = 0;
+    spec = 1;
   }
 
   // nl2sno fresh start (toms573.f90:688-700): D = 1 for the first finite-difference Jacobian.
@@ -172,6 +180,7 @@ struct Nl2 {
     FMC_SOLVER_LOOP
     for (int i = 0; i < P; ++i) hJ[i] = hA[i];
     need_b = 0;
+    need_jac = 1;
     phase = PH_INIT;
     rc = 0;
   }
@@ -1377,7 +1386,7 @@ FMC_HD bool Nl2<P>::resume(unsigned int lanes) {
         if (t > k::rlimit) toobig = 1;
         if (toobig == 0) v[F] = 0.5 * res_f;
         if (phase == PH_TRIAL) {
-          x_is_eval = 1;
+          x_is_eval = spec;  // (spec = 0: the pass evaluated the residual sum alone)
           st = ST_ASSESS;
           break;
         }
@@ -1468,7 +1477,8 @@ FMC_HD bool Nl2<P>::resume(unsigned int lanes) {
         nfcall = nfcall + 1;
         toobig = 0;
         set_fd_steps();
-        need_b = 1;
+        need_b = spec;
+        need_jac = spec;
         phase = PH_TRIAL;
         more = true;
         st = ST_DONE;
@@ -1558,6 +1568,7 @@ FMC_HD bool Nl2<P>::resume(unsigned int lanes) {
           // J(x0)^T r(x) need a pass of their own.
           set_fd_steps();
           need_b = 1;
+          need_jac = 1;
           phase = PH_JAC;
           more = true;
           st = ST_DONE;

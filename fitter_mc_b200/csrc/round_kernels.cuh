@@ -50,15 +50,18 @@ namespace fmc {
 #endif
 
 // ctl words
-enum { RC_ROUND = 0, RC_COUNTS = 1, RC_DONE = 5, RC_ROUNDS_TOTAL = 6, RC_ERROR = 7, RC_NWORDS = 8 };  // counts: [parity][kind]
+enum { RC_KINDS = 3 };  // what a slot asks for: 0 = pass with the J(x0)^T r(x) part, 1 = without, 2 = the residual sum alone
+enum { RC_ROUND = 0, RC_COUNTS = 1, RC_DONE = 1 + 2 * RC_KINDS, RC_ROUNDS_TOTAL = 2 + 2 * RC_KINDS, RC_ERROR = 3 + 2 * RC_KINDS,
+       RC_NWORDS = 4 + 2 * RC_KINDS };  // counts: [parity][kind]
 
 struct RoundArgs {
   long long nslots;            // C: slots of the pool
   unsigned long long* state;   // [W][C]   solver state images (Nl2<P> as 64-bit words), word-major
   long long* slot_fit;         // [C]      chunk-local index of the fit in the slot, < 0 = idle
   int* slot_meta;              // [2][C]   0 = nl2sno call of fit_data the fit is in, 1 = passes of that call so far
-  int* list;                   // [2][2][C] slots that want a pass: [parity of the round][with B, without][.]
+  int* list;                   // [2][RC_KINDS][C] slots that want a pass: [parity of the round][kind][.]
   unsigned int* ctl;           // [RC_NWORDS]
+  int spec;                    // Nl2::spec of the fits: 1 = Jacobian with every trial point, 0 = residual sum first
 };
 
 template <int P>
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(SolveCfg<M::NPARAM>::THREADS) round_solve_kern
 #pragma unroll
         for (int i = 0; i < P; ++i) xs[i] = ap->start[i];
         s.reset_fit();
+        s.spec = ra.spec;
         s.begin(xs);
         s.res_f = ap->init[fit];
         FMC_SOLVER_LOOP
@@ -265,9 +269,9 @@ __global__ void __launch_bounds__(SolveCfg<M::NPARAM>::THREADS) round_solve_kern
   ra.slot_meta[slot] = call;
   ra.slot_meta[C + slot] = fit_passes;
   const unsigned int par = round & 1u;
-  const unsigned int kind = s.need_b ? 0u : 1u;
-  const unsigned int pos = atomicAdd(&ra.ctl[RC_COUNTS + 2 * par + kind], 1u);
-  ra.list[(size_t)(2 * par + kind) * C + pos] = (int)slot;
+  const unsigned int kind = !s.need_jac ? 2u : (s.need_b ? 0u : 1u);
+  const unsigned int pos = atomicAdd(&ra.ctl[RC_COUNTS + RC_KINDS * par + kind], 1u);
+  ra.list[(size_t)(RC_KINDS * par + kind) * C + pos] = (int)slot;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -278,15 +282,15 @@ __global__ void round_ctl_kernel(const RoundArgs ra, cudaGraphConditionalHandle 
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const unsigned int round = ra.ctl[RC_ROUND];
   const unsigned int par = round & 1u;
-  unsigned int n = ra.ctl[RC_COUNTS + 2 * par] + ra.ctl[RC_COUNTS + 2 * par + 1];
+  unsigned int n = 0u;
+  for (int kk = 0; kk < RC_KINDS; ++kk) n += ra.ctl[RC_COUNTS + RC_KINDS * par + kk];
   // a chunk needs at most (passes per call cap) x 2 calls rounds; whatever happens, the loop ends
   const bool runaway = n != 0u && round > 4u * (unsigned int)(k::mxfcal + k::mxiter) + 16u;
   if (runaway) {
     n = 0u;
     ra.ctl[RC_ERROR] = 1u;
   }
-  ra.ctl[RC_COUNTS + 2 * (par ^ 1u)] = 0u;
-  ra.ctl[RC_COUNTS + 2 * (par ^ 1u) + 1] = 0u;
+  for (int kk = 0; kk < RC_KINDS; ++kk) ra.ctl[RC_COUNTS + RC_KINDS * (par ^ 1u) + kk] = 0u;
   ra.ctl[RC_ROUND] = round + 1u;
   ra.ctl[RC_DONE] = n == 0u ? 1u : 0u;
   ra.ctl[RC_ROUNDS_TOTAL] += 1u;
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(FMC_ROUND_PASS_THREADS, (M::NPARAM <= 6 ? 3 : 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long C = ra.nslots;
   const unsigned int par = (ra.ctl[RC_ROUND] - 1u) & 1u;  // (the control kernel has advanced the counter)
-  const unsigned int nA = ra.ctl[RC_COUNTS + 2 * par], nN = ra.ctl[RC_COUNTS + 2 * par + 1];
+  const unsigned int nA = ra.ctl[RC_COUNTS + RC_KINDS * par], nN = ra.ctl[RC_COUNTS + RC_KINDS * par + 1];
   const unsigned int blocksA = (nA + FMC_ROUND_PASS_THREADS - 1) / FMC_ROUND_PASS_THREADS;
   // blocks [0, blocksA) take the list "with B", the following ones the list "without"; the rest exit
   const bool with_b = blockIdx.x < blocksA;
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(FMC_ROUND_PASS_THREADS, (M::NPARAM <= 6 ? 3 : 
   const RowData* rows = stage_rows<SMEM, model_naux<M>::value>(a, smem_raw, &aux);
   const unsigned int idx = b * FMC_ROUND_PASS_THREADS + threadIdx.x;
   if (idx >= cnt) return;
-  const long long slot = ra.list[(size_t)(2 * par + (with_b ? 0 : 1)) * C + idx];
+  const long long slot = ra.list[(size_t)(RC_KINDS * par + (with_b ? 0 : 1)) * C + idx];
   double* img = reinterpret_cast<double*>(ra.state) + slot;  // word w of the image: img[w * C]
   double x[P], h[P], x0[P], h0[P];
 #pragma unroll
@@ -358,6 +362,67 @@ __global__ void __launch_bounds__(FMC_ROUND_PASS_THREADS, (M::NPARAM <= 6 ? 3 : 
   }
 #pragma unroll
   for (int i = 0; i < PP; ++i) img[(long long)(L::RES_GG + i) * C] = G[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// The residual sum alone at a trial point (list kind 2; RoundArgs::spec = 0): the model value per row and
+// f += r^2, accumulated in the order of pass_loop, so that the solver reads the same f as from a full
+// pass.  No Jacobian: few registers, many resident warps.  Used where a Jacobian row costs many model
+// evaluations' worth (p = 10: a full trial pass is ~10x this), so that the passes nobody needed the
+// Jacobian of -- rejected steps, the last step of each nl2sno call -- cost a tenth.
+#ifndef FMC_ROUND_FONLY_THREADS
+#define FMC_ROUND_FONLY_THREADS 256
+#endif
+template <class M, bool INJECT, bool SMEM>
+__global__ void __launch_bounds__(FMC_ROUND_FONLY_THREADS) round_fonly_kernel(const KernelArgs* __restrict__ ap,
+                                                                              const RoundArgs ra) {
+  constexpr int P = M::NPARAM;
+  constexpr int NAUX = model_naux<M>::value;
+  using L = StateLayout<P>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long C = ra.nslots;
+  const unsigned int par = (ra.ctl[RC_ROUND] - 1u) & 1u;
+  const unsigned int cnt = ra.ctl[RC_COUNTS + RC_KINDS * par + 2];
+  if ((unsigned long long)blockIdx.x * FMC_ROUND_FONLY_THREADS >= cnt) return;
+  const KernelArgs a = *ap;
+  const double* aux = nullptr;
+  const RowData* rows = stage_rows<SMEM, NAUX>(a, smem_raw, &aux);
+  const unsigned int idx = blockIdx.x * FMC_ROUND_FONLY_THREADS + threadIdx.x;
+  if (idx >= cnt) return;
+  const long long slot = ra.list[(size_t)(RC_KINDS * par + 2) * C + idx];
+  double* img = reinterpret_cast<double*>(ra.state) + slot;
+  double x[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) x[i] = img[(long long)(L::X + i) * C];
+  const long long fit = ra.slot_fit[slot];
+  const unsigned long long id = (unsigned long long)(a.first + fit);
+  const double* zrow = INJECT ? a.z_inject + (unsigned long long)fit * a.n : nullptr;
+  double f = 0.0;
+  auto row = [&](int r, float zf) {
+    const RowData rd = rows[r];
+    const double zz = INJECT ? zrow[r] : (double)zf;
+    const double yfit = fma(zz, rd.err, rd.y);  // offset_data, bootstrap.f90:208
+    const double* ra_ = NAUX > 0 ? aux + r * NAUX : nullptr;
+    if (NAUX > 0) __builtin_assume(ra_ != nullptr);
+    const double m0 = eval_model<M>(x, rd.x, ra_);
+    const double res = (yfit - m0) * rd.rerr;   // madr, bootstrap.f90:247
+    f = fma(res, res, f);
+  };
+  const int n4 = a.n & ~3;
+  for (int i = 0; i < n4; i += 4) {
+    float z[4];
+    if (!INJECT) normals4(a.seed, id, (uint32_t)(i >> 2), z);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) row(i + m, z[m]);
+  }
+  if (n4 < a.n) {
+    float z[4];
+    if (!INJECT) normals4(a.seed, id, (uint32_t)(n4 >> 2), z);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      if (n4 + m < a.n) row(n4 + m, z[m]);
+  }
+  img[(long long)L::RES_F * C] = f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -477,6 +542,10 @@ struct RoundBinding {
       if (e != cudaSuccess) return e;
       round_pass_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>
           <<<pgrid, FMC_ROUND_PASS_THREADS, shmem, st>>>(ap, ra);
+      e = cudaGetLastError();
+      if (e != cudaSuccess || ra.spec != 0) return e;
+      const unsigned int fgrid = (unsigned int)(ra.nslots / FMC_ROUND_FONLY_THREADS + 1);
+      round_fonly_kernel<M, decltype(I)::value, decltype(S)::value><<<fgrid, FMC_ROUND_FONLY_THREADS, shmem, st>>>(ap, ra);
       return cudaGetLastError();
     });
   }
@@ -492,6 +561,9 @@ struct RoundBinding {
                                  (int)SolveCfg<M::NPARAM>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
       }
+      e = cudaFuncSetAttribute(round_fonly_kernel<M, decltype(I)::value, decltype(S)::value>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+      if (e != cudaSuccess) return e;
       auto kern = round_pass_kernel<M, decltype(I)::value, decltype(S)::value, decltype(J)::value>;
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
       if (e != cudaSuccess) return e;

@@ -198,6 +198,8 @@ int fmc_set_fit_mapping(fmc_context* ctx, int mapping);
  * graph WHILE node; fits that want another pass are compacted into lists between rounds
  * (DESIGN.md 2.8).  Same solver source and the same per-fit sequence of operations; the two compile it
  * differently, so a small share of the fits differs in the last bits (tests/test_round_schedule.py).
+ * Under the round schedule with nparam > 6 a trial point gets its residual sum alone first and its Jacobian only
+ * if the step is accepted and the call goes on (bit-identical fits, fewer Jacobians; FMC_ROUND_SPECULATE=0|1).
  * FMC_SCHEDULE_AUTO (default): by measurement -- rounds when the data rows do not fit in shared memory
  * or nparam > 6 (C4: +19 %), refill otherwise (C1, C2).  Strongly diverging fits (C5: +19 % with rounds)
  * cannot be recognised beforehand; choose FMC_SCHEDULE_ROUNDS for them.  The environment variable

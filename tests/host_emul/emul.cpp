@@ -36,6 +36,8 @@ using namespace fmc;
 
 namespace {
 
+int g_spec = 1;  // Nl2::spec of the fits that follow (emul_set_spec): 1 = Jacobian with every trial point, 0 = residual sum first
+
 template <class M, int JAC = JAC_FD>
 void run_pass(Nl2<M::NPARAM>& s, int n, const double* x, const double* yfit, const double* rerr) {
   constexpr int P = M::NPARAM;
@@ -66,6 +68,7 @@ int fit_one(int n, const double* x, const double* yfit, const double* err, doubl
   Nl2<P> s;
   std::memset(&s, 0, sizeof(s));
   s.reset_fit();
+  s.spec = g_spec;  // (the host pass below always evaluates everything; spec = 0 only changes what the solver asks for and reads)
   for (int pass = 0; pass < 2; ++pass) {
     s.begin(params);
     int npass = 0;
@@ -329,6 +332,8 @@ static_assert(!can_analytic_v<ModelPlainOnly> && !use_pert_v<ModelPlainOnly>, "d
 }  // namespace
 
 extern "C" {
+
+void emul_set_spec(int spec) { g_spec = spec ? 1 : 0; }
 
 // jac = 0: forward differences (nl2sno), 1: analytic (nl2sol + madj).  model 100 = the
 // double-only test plug-in with a hand-written model_grad (same formula as model 0).

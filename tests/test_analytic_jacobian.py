@@ -33,7 +33,7 @@ def emul():
     so = os.path.join(EMUL_DIR, "libfmc_emul.so")
     src = os.path.join(EMUL_DIR, "emul.cpp")
     csrc = os.path.join(os.path.dirname(HERE), "fitter_mc_b200", "csrc")
-    deps = [src] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs if f.endswith(".cuh")]
+    deps = [src] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs if f.endswith((".cuh", ".inc"))]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-x", "c++", "-std=c++17", "-fPIC", "-shared", "-w", "-o", so, src])
     L = C.CDLL(so)

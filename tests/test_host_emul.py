@@ -28,7 +28,7 @@ def emul():
     so = os.path.join(EMUL_DIR, "libfmc_emul.so")
     src = os.path.join(EMUL_DIR, "emul.cpp")
     csrc = os.path.join(os.path.dirname(HERE), "fitter_mc_b200", "csrc")
-    deps = [src] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs if f.endswith(".cuh")]
+    deps = [src] + [os.path.join(dp, f) for dp, _, fs in os.walk(csrc) for f in fs if f.endswith((".cuh", ".inc"))]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-x", "c++", "-std=c++17", "-fPIC", "-shared", "-w", "-o", so, src])
     L = C.CDLL(so)
@@ -180,3 +180,36 @@ def test_every_operation_of_pert_and_dual_against_multiprecision(emul):
           % (worst_pert, worst_plain, worst_dual))
     assert worst_pert < 5e-13 and worst_dual < 5e-13                # cancellation between the terms of the model
     assert worst_plain > 1e3 * worst_pert                           # what the engine avoids
+
+
+@pytest.mark.parametrize("name,nres,jac", [("c1", 300, 0), ("c2", 120, 0), ("c2", 60, 1), ("c5mild", 80, 0), ("c5", 60, 0),
+                                          ("c4", 6, 0)])
+def test_residual_first_mode_takes_the_same_decisions(emul, oracle, name, nres, jac):
+    """Nl2::spec = 0 (the round schedule for many parameters): a trial point gets its residual sum alone
+    first, and only an accepted step that does not end the call asks for the Jacobian pass.  The solver
+    then reads the same numbers in the same order as with the Jacobian evaluated at every trial point, so
+    the fits -- parameters, return codes, evaluation and iteration counts -- are identical bit for bit;
+    only the number of passes differs (one more per accepted, continuing step)."""
+    from test_analytic_jacobian import _emul_run
+
+    model, x, y, err = datasets.dataset(name)
+    info = oracle.model_info(model)
+    start = datasets.C5_FITTED.copy() if name == "c5" else oracle.fit_data(model, x, y, err, info["params_init"])[0]
+    z = np.random.default_rng(77).normal(size=(nres, len(x)))
+    emul.emul_set_spec.argtypes = [C.c_int]
+    emul.emul_bootstrap_jac.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, _dp, _dp, _dp,
+                                        _ip, _ip]
+    try:
+        emul.emul_set_spec(1)
+        p1, q1, c1, a1 = _emul_run(emul, model, jac, x, y, err, start, z, info["nparam"], info["nprop"])
+        emul.emul_set_spec(0)
+        p0, q0, c0, a0 = _emul_run(emul, model, jac, x, y, err, start, z, info["nparam"], info["nprop"])
+    finally:
+        emul.emul_set_spec(1)
+    assert np.array_equal(p1, p0) and np.array_equal(q1, q0)
+    assert np.array_equal(c1[:, :, :4], c0[:, :, :4]) and np.array_equal(a1, a0)
+    extra = (c0[:, :, 4] - c1[:, :, 4]).sum(1)
+    print("\n[residual first %s] %d fits identical; passes per fit %.2f -> %.2f, of which with a Jacobian %.2f -> %.2f"
+          % (name, nres, c1[:, :, 4].sum(1).mean(), c0[:, :, 4].sum(1).mean(), c1[:, :, 4].sum(1).mean(),
+             2 + extra.mean()))
+    assert (extra >= 0).all()
