@@ -13,9 +13,13 @@ MODULE fmc_b200_bindings
   PRIVATE
   PUBLIC :: fmc_bootstrap_run, fmc_bootstrap_run_binned, fmc_fit_once, fmc_generate_offsets, &
     &fmc_strerror_f, fmc_model_count, fmc_set_jacobian_mode, fmc_histogram_quantiles, &
-    &fmc_default_seed
+    &fmc_set_schedule, fmc_last_combine_method, fmc_default_seed, &
+    &fmc_schedule_refill, fmc_schedule_rounds, fmc_schedule_auto
 
   INTEGER(c_long_long), PARAMETER :: fmc_default_seed = 31415_c_long_long ! utils.f90:7
+  ! fmc_set_schedule (include/fmc_b200.h): how the iterations of the fits are scheduled on the GPU
+  INTEGER(c_int), PARAMETER :: fmc_schedule_refill = 0_c_int, fmc_schedule_rounds = 1_c_int, &
+    &fmc_schedule_auto = 2_c_int
 
   INTERFACE
 
@@ -66,6 +70,23 @@ MODULE fmc_b200_bindings
       INTEGER(c_int), VALUE :: mode
       INTEGER(c_int) :: rc
     END FUNCTION fmc_set_jacobian_mode
+
+    ! No counterpart in the reference: one persistent kernel with refill, or solver steps and passes as
+    ! separate kernels in rounds; fmc_schedule_auto (the default) chooses by measurement.  Results agree
+    ! to the parity floor.  ctx = c_null_ptr sets it for fmc_bootstrap_run / fmc_fit_once.
+    FUNCTION fmc_set_schedule(ctx, schedule) BIND(C, name='fmc_set_schedule') RESULT(rc)
+      IMPORT :: c_int, c_ptr
+      TYPE(c_ptr), VALUE :: ctx
+      INTEGER(c_int), VALUE :: schedule
+      INTEGER(c_int) :: rc
+    END FUNCTION fmc_set_schedule
+
+    ! How the last fmc_bootstrap_run with ngpus > 1 combined the GPUs' moment blocks: 1 = one
+    ! ncclAllReduce over NVLink (the REDUCTION(+) of bootstrap.f90:310-311), 0 = one GPU, 2 = summed on the host.
+    FUNCTION fmc_last_combine_method() BIND(C, name='fmc_last_combine_method') RESULT(method)
+      IMPORT :: c_int
+      INTEGER(c_int) :: method
+    END FUNCTION fmc_last_combine_method
 
     ! Quantiles of one quantity from its column of counts.
     FUNCTION fmc_histogram_quantiles(counts, nbins, lo, hi, probs, nprobs, out) &
