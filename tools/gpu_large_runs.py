@@ -13,7 +13,7 @@ for name, nres in [("c2", 100_000_000), ("c2p3", 10_000_000), ("c5", 10_000_000)
         continue
     model, x, y, err = datasets.dataset(name)
     info = oracle.model_info(model)
-    start, _ = oracle.fit_data(model, x, y, err, info["params_init"])
+    start = datasets.C5_FITTED.copy() if name == "c5" else oracle.fit_data(model, x, y, err, info["params_init"])[0]
     ctx = fmc.Context(0)
     ctx.set_data(model, x, y, err)
     t0 = time.perf_counter()
@@ -25,7 +25,8 @@ for name, nres in [("c2", 100_000_000), ("c2p3", 10_000_000), ("c5", 10_000_000)
     qm, qs = fmc.finalise_moments(nres, res["sum_prop"], res["sum_prop2"])
     rec = dict(config=name, n=len(x), p=info["nparam"], nresample=nres, kernel_ms=ms, wall_s=wall,
                fits_per_s=nres / ms * 1e3, mean=mean.tolist(), sd=sd.tolist(), prop_mean=qm.tolist(), prop_sd=qs.tolist(),
-               rc_count=res["rc_count"][3:11].tolist(), per_fit=(res["totals"] / nres).tolist(), fitted=start.tolist())
+               rc_count=res["rc_count"][3:11].tolist(), per_fit=(res["totals"] / nres).tolist(), fitted=start.tolist(),
+               schedule=ctx.schedule(), safety_cap_hits=int(ctx.anomalies()[2]))
     out[name] = rec
     print(json.dumps(rec))
     ctx.close()
