@@ -38,7 +38,9 @@ def test_sm_100a_only(usage):
     assert archs == {"100a"}, archs                                  # written for B200 only, no other targets
 
 
-@pytest.mark.parametrize("model,solver_stack", [("9ModelUser", 1240), ("10ModelTest4", 1648), ("11ModelStiff4", 1648)])
+# (the stress model is built with the compact, all-rolled solver -- csrc/kernels_model3.cu: 32 bytes more frame for
+# the out-of-line helpers' arguments, still no spill in the row loop)
+@pytest.mark.parametrize("model,solver_stack", [("9ModelUser", 1240), ("10ModelTest4", 1648), ("11ModelStiff4", 1680)])
 def test_refill_kernels_of_small_models_do_not_spill(usage, model, solver_stack):
     # iterate_kernel<M, INJECT=0, SMEM=1, JAC_FD>: the kernel bench.py times
     regs, stack = _find(usage, "iterate_kernelINS_" + model + "ELb0ELb1ELi0EEEv")
