@@ -179,3 +179,18 @@ def test_rounds_per_fit_parity_with_the_oracle(oracle):
     print("\n[rounds parity c2] median %.2e p99 %.2e max %.2e" % (np.median(rel), np.quantile(rel, 0.99), rel.max()))
     assert np.median(rel) <= 5e-9 and rel.max() <= 1e-7
     assert np.allclose(got["sum_p"], want["sum_p"], rtol=1e-9)
+
+
+def test_schedule_setting_argument_checks():
+    """No GPU needed: the setting is validated and kept per process for the one-call entry points."""
+    import fitter_mc_b200 as fmc
+
+    L = fmc.lib()
+    try:
+        for code in (0, 1, 2):          # FMC_SCHEDULE_REFILL, _ROUNDS, _AUTO
+            assert L.fmc_set_schedule(None, code) == 0
+            assert L.fmc_get_schedule(None) == code
+        assert L.fmc_set_schedule(None, 3) == -4 and L.fmc_set_schedule(None, -1) == -4   # FMC_ERR_BAD_ARG
+        assert L.fmc_get_schedule(None) == 2
+    finally:
+        L.fmc_set_schedule(None, 2)
