@@ -488,7 +488,10 @@ def main():
                          "note": "FP64-FMA bound (SURVEY.md 8d), not hbm/tensor; peak = DFMA-chain microbenchmark "
                                  "measured in this run; achieved = %.0f algorithmic flops/fit x kernel fits/s; "
                                  "hw_counted_tflops / traffic = ncu counters of the dominant kernel, per launch, from "
-                                 "the committed capture named in ncu_source" % w_fit},
+                                 "the committed capture named in ncu_source; achieved counts the REFERENCE algorithm's "
+                                 "operations (one Jacobian per gradient call it makes), so it exceeds the hardware count "
+                                 "and can exceed the peak where the engine skips Jacobians nobody reads (round schedule "
+                                 "with the residual sum first, DESIGN.md 2.8)" % w_fit},
         }
         if checks:
             line["checks"] = checks
