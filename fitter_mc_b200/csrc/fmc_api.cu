@@ -936,9 +936,9 @@ int fmc_launch(fmc_context* c, const double* params_start, long long nresample, 
   // FMC_SCHEDULE_AUTO, by measurement (profiles/r2_schedule_*.json): the round schedule wins where the pass
   // kernel gains from shedding the solver's state -- rows that do not fit in shared memory, or so many
   // parameters that the row loop needs every register (C4: n = 10^4, p = 10, +19 %) -- and loses on
-  // small, well-behaved fits (C1, C2: the solve kernel's trip through HBM costs more than the divergence
-  // it removes).  Strongly diverging fits (C5) also gain (+19 %), but that is not knowable beforehand:
-  // set FMC_SCHEDULE_ROUNDS for them.
+  // small fits (C1, C2: the solve kernel's trip through HBM costs more than the divergence it removes; C5,
+  // whose fits diverge strongly: rounds won until the refill kernel's solver was compiled compactly for
+  // that model, csrc/kernels_model3.cu -- 8.2e5 against 6.4e5 fits/s).
   const int schedule = c->schedule == FMC_SCHEDULE_AUTO ? ((!smem || P > 6) ? FMC_SCHEDULE_ROUNDS : FMC_SCHEDULE_REFILL)
                                                         : c->schedule;
   c->schedule_used = schedule;

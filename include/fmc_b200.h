@@ -201,8 +201,9 @@ int fmc_set_fit_mapping(fmc_context* ctx, int mapping);
  * Under the round schedule with nparam > 6 a trial point gets its residual sum alone first and its Jacobian only
  * if the step is accepted and the call goes on (bit-identical fits, fewer Jacobians; FMC_ROUND_SPECULATE=0|1).
  * FMC_SCHEDULE_AUTO (default): by measurement -- rounds when the data rows do not fit in shared memory
- * or nparam > 6 (C4: +19 %), refill otherwise (C1, C2).  Strongly diverging fits (C5: +19 % with rounds)
- * cannot be recognised beforehand; choose FMC_SCHEDULE_ROUNDS for them.  The environment variable
+ * or nparam > 6 (C4: +19 %), refill otherwise (C1, C2, and C5 -- strongly diverging fits -- once the model's
+ * translation unit is built with the compact solver, csrc/kernels_model3.cu: 8.2e5 against 6.4e5 fits/s).
+ * The environment variable
  * FMC_SCHEDULE=refill|rounds overrides the default.  ctx = NULL sets it for the one-call entry points.
  * fmc_get_schedule returns the setting, or, for AUTO, what the last launch resolved it to. */
 #define FMC_SCHEDULE_REFILL 0
